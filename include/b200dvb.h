@@ -1,0 +1,160 @@
+/*
+ * b200dvb.h — C ABI of libb200dvb.so: the B200 (sm_100a) implementation of the
+ * baseband decode hot path of poriya219/modulations.
+ *
+ * The reference has no FFI of its own (it is pure Python + numba); the boundary
+ * is the set of Python callables listed in SURVEY.md §8(b).  Each entry point
+ * below names the reference callable(s) it sits under (file:line in the
+ * reference tree).  modulations_b200/ binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in _h (host).
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL =
+ *    the legacy default stream).  No entry point synchronises the device.
+ *  - The caller owns every buffer, including the workspaces whose sizes the
+ *    *_workspace_bytes queries return.
+ *  - Return value: 0 on success, a negative B200DVB_E* code otherwise.
+ *    b200dvb_error_string() maps codes to text; B200DVB_ECUDA keeps the CUDA
+ *    error retrievable with b200dvb_last_cuda_error().
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    returns B200DVB_ECUDA.
+ */
+#ifndef B200DVB_H
+#define B200DVB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DVB_OK        0
+#define B200DVB_EINVAL   -1   /* bad argument (NULL pointer, negative size, ...)            */
+#define B200DVB_ENOSPEC  -2   /* tables/sizes this build has no kernel specialisation for   */
+#define B200DVB_ECUDA    -3   /* a CUDA runtime call or launch failed                       */
+#define B200DVB_ENOMEM   -4   /* workspace too small / allocation failed                    */
+#define B200DVB_EMOD     -5   /* unknown modulation id  (reference: ValueError)             */
+
+/* modulation ids: SDRModem.MODULATIONS, sdr_modem.py:29-36 */
+#define B200DVB_BPSK    0
+#define B200DVB_QPSK    1
+#define B200DVB_8PSK    2
+#define B200DVB_16QAM   3
+#define B200DVB_64QAM   4
+#define B200DVB_256QAM  5
+
+int         b200dvb_version(void);
+const char *b200dvb_error_string(int code);
+const char *b200dvb_last_cuda_error(void);
+int         b200dvb_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Turbo codec handle.  Replaces DVBRCS2_Turbo.__init__ (dvb_rcs2_turbo.py:
+ * 287-309): the host computes the tables exactly as the reference does
+ * (_init_interleaver :311-325, _init_trellis :327-396, PUNCTURE_PATTERNS :21-26)
+ * and hands them over as opaque data — perm / inv_perm are NOT assumed to be
+ * permutations.
+ *   next_state_h, out_W_h, out_Y_h : int32[16*4]   (:333-370)
+ *   perm_h, inv_perm_h             : int32[N]      (:314-325)
+ *   punct_h                        : uint8[4*period], rows W1,Y1,W2,Y2 (:21-26)
+ *   sf_inner / sf_last             : extrinsic scaling 0.7 / 1.0 (:496)
+ * Returns B200DVB_ENOSPEC if the trellis is not the 16-state butterfly the
+ * kernels are specialised for, or if N is not a multiple of 4 in [12, 2048].
+ * ---------------------------------------------------------------------- */
+typedef struct b200dvb_codec *b200dvb_codec_t;
+
+int b200dvb_codec_create(int N, const int32_t *next_state_h, const int32_t *out_W_h,
+                         const int32_t *out_Y_h, const int32_t *perm_h,
+                         const int32_t *inv_perm_h, const uint8_t *punct_h, int period,
+                         int iterations, double sf_inner, double sf_last,
+                         b200dvb_codec_t *out);
+int b200dvb_codec_destroy(b200dvb_codec_t codec);
+/* LLRs the depuncturer consumes per frame (= bits the encoder emits; differs
+ * from the reference's n_coded when N % period != 0, dvb_rcs2_turbo.py:398-402) */
+int b200dvb_codec_n_llr(b200dvb_codec_t codec);
+
+/* One SISO half-iteration for B independent frames.  Replaces bcjr_max_log_map
+ * (dvb_rcs2_turbo.py:116-281; historic aliases bcjr_decode_circular /
+ * max_log_map_decode).  Lc_* float32[B*N], La_* float64[B*N] (NULL = zeros),
+ * Le_* float64[B*N].  Bit-exact with the reference's mixed fp64/fp32 arithmetic. */
+size_t b200dvb_siso_workspace_bytes(b200dvb_codec_t codec, int B);
+int b200dvb_siso(b200dvb_codec_t codec, int B, const float *Lc_A, const float *Lc_B,
+                 const float *Lc_W, const float *Lc_Y, const double *La_A, const double *La_B,
+                 double scaling_factor, double *Le_A, double *Le_B, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
+/* Full decode of B frames: depuncture -> iterations x (SISO1, interleave, SISO2,
+ * de-interleave) -> hard decision.  Replaces DVBRCS2_Turbo.decode
+ * (dvb_rcs2_turbo.py:464-537).
+ *   llr       float32[B][llr_stride], the first n_llr of each row are used
+ *   bits      int32[B][2N]  (reference layout :532-535) or NULL
+ *   packed    uint32[B][ceil(2N/32)], bit i of the frame at word i/32, bit i%32, or NULL
+ *   ref_bits  uint8[B][2N] transmitted info bits for error counting, or NULL
+ *   counters  uint64[4] += {bit errors, frame errors, frames, info bits}, or NULL
+ *             (accumulated with atomicAdd; this is what the multi-GPU harness
+ *             all-reduces) */
+size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B);
+int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr_stride,
+                   int32_t *bits, uint32_t *packed, const uint8_t *ref_bits,
+                   unsigned long long *counters, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* Tail-biting encoder for B frames.  Replaces DVBRCS2_Turbo.encode
+ * (dvb_rcs2_turbo.py:431-462) including _encode_component (:404-429) and the
+ * GF(2) circular-state solve mat_pow_gf2 / solve_circular_state_gf2 (:50-114).
+ *   info  uint8[B][2N] -> coded uint8[B][n_llr];  circ (nullable) uint8[B][2]
+ *   receives the two circular start states. */
+int b200dvb_encode(b200dvb_codec_t codec, int B, const uint8_t *info, uint8_t *coded,
+                   uint8_t *circ, void *stream);
+/* Sc = (I + G^N)^-1 Z for every Z in 0..15: the bit-packed GF(2) solve as a
+ * host-visible table (solve_circular_state_gf2, dvb_rcs2_turbo.py:63-114). */
+int b200dvb_codec_circular_lut(b200dvb_codec_t codec, int32_t *lut16_h);
+
+/* ------------------------------------------------------------------------
+ * Mapper / slicer / soft demapper.  `table` = constellation indexed by the
+ * MSB-first bit label: double[2*M] (re,im) on the HOST, as produced by the
+ * reference mapper on all labels (test_sdr_with_coding.py:207-208).
+ * ---------------------------------------------------------------------- */
+typedef struct b200dvb_modem *b200dvb_modem_t;
+int b200dvb_modem_create(int mod_id, const double *table_h, b200dvb_modem_t *out);
+int b200dvb_modem_destroy(b200dvb_modem_t modem);
+
+/* bits uint8[n_sym*bps] (caller zero-pads, sdr_modem.py:122-124) -> symbols.
+ * Replaces SDRModem.modulate (sdr_modem.py:222-243).  out_f64 = 0: float2
+ * (complex64), 1: double2 (complex128, the dtype the reference returns for QPSK). */
+int b200dvb_map(b200dvb_modem_t modem, size_t n_sym, const uint8_t *bits, void *iq,
+                int out_f64, void *stream);
+/* Max-log bit LLRs, clipped to +-30, positive = bit 1.  Replaces compute_llr
+ * (test_sdr_with_coding.py:200-225).  iq float2[n_sym] -> llr float32[n_sym*bps];
+ * noise_var is floored at 0.005 (:202).  `scale` multiplies the clipped LLR
+ * (use -1 to feed the decoder, whose convention is positive = bit 0). */
+int b200dvb_demap(b200dvb_modem_t modem, size_t n_sym, const void *iq, float noise_var,
+                  float scale, float *llr, void *stream);
+/* Hard decisions.  Replaces SDRModem.demodulate (sdr_modem.py:245-266) and
+ * Modulator._demod_qam_generic (modulators.py:165-171): nearest constellation
+ * point, evaluated in float64.  in_f64 selects float2 / double2 input. */
+int b200dvb_hard_demod(b200dvb_modem_t modem, size_t n_sym, const void *iq, int in_f64,
+                       uint8_t *bits, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Monte-Carlo source (harness shape of turbo_test_suite.py:121-199, test.py:
+ * 34-103): Philox-seeded info bits, encode, BPSK/QPSK/.. map, AWGN, LLR — all on
+ * device, written straight into the decoder's input layout.
+ *   info_out uint8[B][2N]; coded_out uint8[B][n_llr]; llr_out float32[B][n_llr]
+ *   (contiguous rows).  BPSK: llr = 2y/sigma^2 clipped to +-50
+ *   (turbo_test_suite.py:158-161). */
+int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
+                             unsigned long long seed, unsigned long long frame_offset,
+                             uint8_t *info_out, uint8_t *coded_out, float *llr_out,
+                             void *stream);
+
+/* Small device-throughput probes used by bench.py to state the ALU roofline
+ * (FADD / FMNMX / SHFL lane-ops per clock per SM).  results_h: double[8]. */
+int b200dvb_microbench(double *results_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DVB_H */

@@ -1,0 +1,56 @@
+"""Builds libb200dvb.so in-tree with nvcc for sm_100a (no torch, no JIT cache).
+
+    python -m modulations_b200.build [--force] [--verbose]
+
+The shared library is git-ignored but travels to the GPU box with the repo
+snapshot; `__graft_entry__.build()` calls :func:`build`.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libb200dvb.so")
+SOURCES = ["api.cu", "decode_quad.cu", "encode.cu", "modem.cu", "microbench.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=false",
+    "-ccbin", "g++",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(os.path.dirname(HERE), "include", "b200dvb.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into modulations_b200/libb200dvb.so."""
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if verbose or res.returncode != 0:
+        print(log)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libb200dvb.so (see modulations_b200/build.log)")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or True)

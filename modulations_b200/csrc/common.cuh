@@ -1,0 +1,91 @@
+// common.cuh — shared declarations for libb200dvb.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/b200dvb.h"
+
+namespace b200dvb {
+
+// ---- error plumbing --------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char *where);
+#define B2_CUDA(call)                                                     \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            ::b200dvb::set_cuda_error(e__, #call);                        \
+            return B200DVB_ECUDA;                                         \
+        }                                                                 \
+    } while (0)
+
+constexpr int kMaxN = 2048;
+
+// ---- decoder geometry (decode_quad.cu) --------------------------------------
+constexpr int kFramesPerCta = 8;    // one 4-lane "quad" per frame and direction
+constexpr int kCtaThreads = 64;     // warp 0: forward (alpha), warp 1: backward (beta)
+constexpr int kWin = 8;             // checkpoint spacing / recompute window (steps)
+
+struct QuadGeom {
+    int N;            // couples per frame
+    int M;            // crossing point: alpha warp owns [M,N), beta warp owns [0,M)
+    int nckA;         // alpha checkpoints (alpha[0], alpha[8], ... alpha[M-8])
+    int nckB;         // beta checkpoints, one per alpha-warp window end
+    int rec_stride;   // floats between two frames' branch-metric records (8N + 8)
+    int ck_stride;    // floats between two frames' checkpoint areas
+    int frames;       // frames per CTA actually used (<= kFramesPerCta)
+    int ctas_per_sm;
+    size_t smem_bytes;
+};
+
+struct Codec {
+    int N = 0, period = 0, iterations = 0, n_llr = 0;
+    double sf_inner = 0.7, sf_last = 1.0;
+    QuadGeom geom{};
+    int num_sms = 0;
+    // device tables
+    int16_t *d_tab = nullptr;     // [7][N] int16: perm, inv_perm, offA, offW1, offY1, offW2, offY2
+    // host tables
+    int32_t next_state[64], out_W[64], out_Y[64];
+    int32_t circ_lut[16];
+    int16_t *h_tab = nullptr;
+};
+
+struct Modem {
+    int mod_id = 0, bps = 0, M = 0;
+    int separable = 0;            // 1: first half of the label selects I, 2: selects Q, 0: not separable
+    int half = 0, nlev = 0;       // bits / levels per axis when separable
+    int pwl = 0;                  // piecewise-linear per-axis demapper usable (uniform PAM axes)
+    int nseg = 0;                 // segments per axis (2*nlev - 2)
+    float pwl_x0[2] = {0, 0}, pwl_invd[2] = {0, 0};   // per axis (0: first half of label, 1: second)
+    double *d_table64 = nullptr;  // double2[M]
+    float *d_table32 = nullptr;   // float2[M]
+    float *d_pwl = nullptr;       // float2[2][half][nseg] (slope, intercept)
+    double h_table[512];
+};
+
+// launchers (each returns a B200DVB_* code)
+int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
+                  uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,
+                  void *ws, size_t ws_bytes, cudaStream_t s);
+int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, const float *Lc_W,
+                const float *Lc_Y, const double *La_A, const double *La_B, double sf,
+                double *Le_A, double *Le_B, void *ws, size_t ws_bytes, cudaStream_t s);
+size_t decode_workspace_bytes(const Codec &c, int B);
+size_t siso_workspace_bytes(const Codec &c, int B);
+int quad_configure(Codec &c);
+
+int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,
+                  cudaStream_t s);
+int launch_mc_bpsk(const Codec &c, int B, float noise_var, unsigned long long seed,
+                   unsigned long long frame_offset, uint8_t *info, uint8_t *coded, float *llr,
+                   cudaStream_t s);
+
+int launch_map(const Modem &m, size_t n, const uint8_t *bits, void *iq, int out_f64, cudaStream_t s);
+int launch_demap(const Modem &m, size_t n, const void *iq, float noise_var, float scale,
+                 float *llr, cudaStream_t s);
+int launch_hard(const Modem &m, size_t n, const void *iq, int in_f64, uint8_t *bits, cudaStream_t s);
+
+int modem_build_pwl(Modem &m);
+int run_microbench(double *results_h);
+
+}  // namespace b200dvb

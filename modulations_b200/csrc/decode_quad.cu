@@ -1,0 +1,611 @@
+// decode_quad.cu — batched max-log-MAP decoder for the 16-state duo-binary
+// circular turbo code, bit-exact with the reference's mixed fp64/fp32 arithmetic
+// (reference: dvb_rcs2_turbo.py:116-281 bcjr_max_log_map, :464-537 decode).
+//
+// Mapping (DESIGN.md §4 has the derivation and the numbers):
+//   * One CTA = 2 warps = 8 frames.  Warp 0 runs the forward (alpha) recursion,
+//     warp 1 the backward (beta) recursion of the same 8 frames.
+//   * One frame and direction = a "quad" of 4 lanes, 4 states per lane.  The
+//     trellis is a shift register (ns = 2*(s&7) + dk), so two trellis steps are
+//     lane-local (a radix-4 butterfly) and the 16 metrics are re-dealt by a 4x4
+//     transpose through shared memory every second step.  The per-step
+//     normalisation by state 0 (:178-179) is a 4-wide shuffle broadcast.
+//   * Branch metrics are kept in shared memory as ONE 32-byte record per step:
+//     the 8 merged values GP[c] = max(g(00), g(11)), GM[c] = max(g(01), g(10)) for
+//     the four (W,Y) classes c.  The reference trellis has parallel branches
+//      and fp32 rounding is monotone, so max(fl(a+g1), fl(a+g2)) ==
+//     fl(a + max(g1,g2)) exactly: the 4-way ACS collapses to 2-way.  The smaller
+//     member of each pair is -GP[~c] / -GM[~c], so the extrinsic stage recovers
+//     all 16 signed branch metrics from the same record.
+//   * The reference stores a full alpha and a full beta array (:163,:200).  Here
+//     the two warps meet in the middle: each stores a checkpoint every 8 steps on
+//     its way in, and on the way out re-computes the other direction 8 steps at a
+//     time into registers (exact: same operations, same order).  Shared memory
+//     per frame is 32 B/step + 2 x 64 B per 8 steps instead of 160 B/step.
+//   * a-priori / extrinsic values stay float64 (:233-234, :267-279) in an
+//     L2-resident global workspace; interleaving is a gather through the host's
+//     perm / inv_perm tables (never assumed bijective).
+#include "common.cuh"
+
+namespace b200dvb {
+
+namespace {
+
+struct QuadArgs {
+    QuadGeom g;
+    int B, iterations, n_groups;
+    double sf_inner, sf_last;
+    const int16_t *tab;
+    // full decode
+    const float *llr;
+    long long llr_stride;
+    int32_t *bits;
+    uint32_t *packed;
+    const uint8_t *ref_bits;
+    unsigned long long *counters;
+    // single SISO
+    const float *LcA, *LcB, *LcW, *LcY;
+    const double *LaA, *LaB;
+    double *LeA, *LeB;
+    double siso_sf;
+    // workspace
+    double2 *Le1, *Le2, *Y;
+};
+
+constexpr int kXchFloats = 144;   // one exchange buffer (8 quads, skewed), see xbase()
+
+__device__ __forceinline__ int cls2(int s)
+{   // 2 * class(s): class = 2*(s0^s1^s2) + s1  (w = A^B^s0^s1^s2, y = A^B^s1)
+    int s0 = s & 1, s1 = (s >> 1) & 1, s2 = (s >> 2) & 1;
+    return 2 * (2 * (s0 ^ s1 ^ s2) + s1);
+}
+
+struct Lane {
+    int q;         // quad (frame within CTA)
+    int p;         // lane within quad
+    int oA[2];     // float offset of butterfly A's (g0,g1) pair inside a record, by parity of k
+    int oB[2];     // same for butterfly B
+    int xw;        // float offset of this lane's float4 slot in an exchange buffer
+    int xr;        // float offset of column p, row 0 of this quad in an exchange buffer
+    int role_word; // record word this lane writes in the extrinsic reduction
+};
+
+// exchange buffer: quad q occupies 16 floats at 16q + 4(q>>1): float4 stores of a
+// quarter-warp and the column reads of a full warp are both bank-conflict free.
+__device__ __forceinline__ int xbase(int q) { return 16 * q + 4 * (q >> 1); }
+
+__device__ __forceinline__ void norm4(float (&r)[4])
+{   // alpha[k+1,:] -= alpha[k+1,0]  (dvb_rcs2_turbo.py:178-179, :212-213)
+    float n = __shfl_sync(0xffffffffu, r[0], 0, 4);
+    r[0] = __fsub_rn(r[0], n); r[1] = __fsub_rn(r[1], n);
+    r[2] = __fsub_rn(r[2], n); r[3] = __fsub_rn(r[3], n);
+}
+
+template <int KPAR>
+__device__ __forceinline__ void step(float (&r)[4], const float *rec, const Lane &L)
+{
+    const float2 gA = *reinterpret_cast<const float2 *>(rec + L.oA[KPAR]);
+    const float2 gB = *reinterpret_cast<const float2 *>(rec + L.oB[KPAR]);
+    float o0 = fmaxf(__fadd_rn(r[0], gA.x), __fadd_rn(r[2], gA.y));
+    float o1 = fmaxf(__fadd_rn(r[0], gA.y), __fadd_rn(r[2], gA.x));
+    float o2 = fmaxf(__fadd_rn(r[1], gB.y), __fadd_rn(r[3], gB.x));
+    float o3 = fmaxf(__fadd_rn(r[1], gB.x), __fadd_rn(r[3], gB.y));
+    r[0] = o0; r[1] = o1; r[2] = o2; r[3] = o3;
+    norm4(r);
+}
+
+// 4x4 transpose inside each quad through shared memory.
+__device__ __forceinline__ void transpose_fwd(float (&r)[4], float *xb, const Lane &L)
+{
+    *reinterpret_cast<float4 *>(xb + L.xw) = make_float4(r[0], r[1], r[2], r[3]);
+    __syncwarp();
+    r[0] = xb[L.xr]; r[1] = xb[L.xr + 4]; r[2] = xb[L.xr + 8]; r[3] = xb[L.xr + 12];
+}
+__device__ __forceinline__ void transpose_bwd(float (&r)[4], float *xb, const Lane &L)
+{   // same transpose applied to the register tuple (r0, r2, r1, r3)
+    *reinterpret_cast<float4 *>(xb + L.xw) = make_float4(r[0], r[2], r[1], r[3]);
+    __syncwarp();
+    r[0] = xb[L.xr]; r[2] = xb[L.xr + 4]; r[1] = xb[L.xr + 8]; r[3] = xb[L.xr + 12];
+}
+
+struct Xch {            // two alternating exchange buffers: one __syncwarp per use
+    float *b0, *b1;
+    __device__ __forceinline__ float *next() { float *t = b0; b0 = b1; b1 = t; return t; }
+};
+
+// alpha[k] -> alpha[k+1] for k, k+1 (k even), ending in boundary layout
+__device__ __forceinline__ void fwd2(float (&r)[4], const float *rec, const Lane &L, Xch &x)
+{
+    step<0>(r, rec, L);
+    step<1>(r, rec + 8, L);
+    transpose_fwd(r, x.next(), L);
+}
+// beta[j] -> beta[j-2] (j even): uses gamma[j-1] (odd) then gamma[j-2] (even)
+__device__ __forceinline__ void bwd2(float (&r)[4], const float *rec_jm2, const Lane &L, Xch &x)
+{
+    step<1>(r, rec_jm2 + 8, L);
+    step<0>(r, rec_jm2, L);
+    transpose_bwd(r, x.next(), L);
+}
+
+// Extrinsic for step k (dvb_rcs2_turbo.py:239-248) fused with the owning
+// direction's recursion step.  a = alpha[k], b = beta[k+1] in matching layouts.
+// Writes (U0, U3, V1, V2) = max over states of the four branch-pair metrics into
+// words 0..3 of record k (gamma[k] is dead after this step).
+template <int KPAR, bool OWN_ALPHA>
+__device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], float *rec, const Lane &L,
+                                         Xch &x)
+{
+    const float2 gA = *reinterpret_cast<const float2 *>(rec + L.oA[KPAR]);
+    const float2 gB = *reinterpret_cast<const float2 *>(rec + L.oB[KPAR]);
+    const float2 hA = *reinterpret_cast<const float2 *>(rec + 6 - L.oA[KPAR]);
+    const float2 hB = *reinterpret_cast<const float2 *>(rec + 6 - L.oB[KPAR]);
+    // butterfly A: x = (a0,a2) y = (b0,b2) g = (gA.x,gA.y) h = (hA.x,hA.y)
+    const float a0g0 = __fadd_rn(a[0], gA.x), a2g0 = __fadd_rn(a[2], gA.x);
+    const float a0g1 = __fadd_rn(a[0], gA.y), a2g1 = __fadd_rn(a[2], gA.y);
+    float AE0 = fmaxf(__fadd_rn(a0g0, b[0]), __fadd_rn(a2g0, b[2]));
+    float AE1 = fmaxf(__fadd_rn(a0g1, b[2]), __fadd_rn(a2g1, b[0]));
+    float AF0 = fmaxf(__fadd_rn(__fsub_rn(a[0], hA.x), b[0]), __fadd_rn(__fsub_rn(a[2], hA.x), b[2]));
+    float AF1 = fmaxf(__fadd_rn(__fsub_rn(a[0], hA.y), b[2]), __fadd_rn(__fsub_rn(a[2], hA.y), b[0]));
+    // butterfly B: x = (a1,a3) y = (b1,b3) g = (gB.y,gB.x) h = (hB.y,hB.x)
+    const float a1g0 = __fadd_rn(a[1], gB.y), a3g0 = __fadd_rn(a[3], gB.y);
+    const float a1g1 = __fadd_rn(a[1], gB.x), a3g1 = __fadd_rn(a[3], gB.x);
+    float BE0 = fmaxf(__fadd_rn(a1g0, b[1]), __fadd_rn(a3g0, b[3]));
+    float BE1 = fmaxf(__fadd_rn(a1g1, b[3]), __fadd_rn(a3g1, b[1]));
+    float BF0 = fmaxf(__fadd_rn(__fsub_rn(a[1], hB.y), b[1]), __fadd_rn(__fsub_rn(a[3], hB.y), b[3]));
+    float BF1 = fmaxf(__fadd_rn(__fsub_rn(a[1], hB.x), b[3]), __fadd_rn(__fsub_rn(a[3], hB.x), b[1]));
+    float4 T;
+    if (KPAR == 0) {   // even k: butterfly B has t = 1 -> its roles are (V1,U0,V2,U3)
+        T = make_float4(fmaxf(AE0, BE1), fmaxf(AE1, BE0), fmaxf(AF0, BF1), fmaxf(AF1, BF0));
+    } else {           // odd k: both butterflies share t = p1 (resolved by the reader)
+        T = make_float4(fmaxf(AE0, BE0), fmaxf(AE1, BE1), fmaxf(AF0, BF0), fmaxf(AF1, BF1));
+    }
+    // own recursion step (shares the x+g sums when the owner is alpha)
+    if (OWN_ALPHA) {
+        float o0 = fmaxf(a0g0, a2g1), o1 = fmaxf(a0g1, a2g0);
+        float o2 = fmaxf(a1g0, a3g1), o3 = fmaxf(a1g1, a3g0);
+        a[0] = o0; a[1] = o1; a[2] = o2; a[3] = o3;
+        norm4(a);
+    } else {
+        float o0 = fmaxf(__fadd_rn(b[0], gA.x), __fadd_rn(b[2], gA.y));
+        float o1 = fmaxf(__fadd_rn(b[0], gA.y), __fadd_rn(b[2], gA.x));
+        float o2 = fmaxf(__fadd_rn(b[1], gB.y), __fadd_rn(b[3], gB.x));
+        float o3 = fmaxf(__fadd_rn(b[1], gB.x), __fadd_rn(b[3], gB.y));
+        b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3;
+        norm4(b);
+    }
+    // cross-lane max: lane p collects role p from the four lanes of its quad.
+    // Roles (U0,V1,U3,V2); on odd k lanes 2,3 (p1 = 1) hold them as (V1,U0,V2,U3).
+    float *xb = x.next();
+    *reinterpret_cast<float4 *>(xb + L.xw) = T;
+    __syncwarp();
+    const int c01 = L.xr, c23 = (KPAR == 1) ? (L.xr ^ 1) : L.xr;
+    float v = fmaxf(fmaxf(xb[c01], xb[c01 + 4]), fmaxf(xb[c23 + 8], xb[c23 + 12]));
+    rec[L.role_word] = v;
+}
+
+// ---------------------------------------------------------------------------
+// One SISO over the 8 frames of this CTA.  Records must be complete and a
+// __syncthreads() must have been executed before the call; on return (after the
+// trailing __syncthreads) words 0..3 of every record hold (U0,U3,V1,V2).
+// ---------------------------------------------------------------------------
+template <int LEN>
+__device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const float *ck, int j0,
+                                             const Lane &L, Xch &x)
+{
+    float wb[LEN][4];
+    {
+        const float4 c = *reinterpret_cast<const float4 *>(ck);
+        wb[LEN - 1][0] = c.x; wb[LEN - 1][1] = c.y; wb[LEN - 1][2] = c.z; wb[LEN - 1][3] = c.w;
+    }
+#pragma unroll
+    for (int i = LEN - 2; i >= 0; --i) {   // beta[j0+2+i] -> beta[j0+1+i] uses gamma[j0+1+i]
+#pragma unroll
+        for (int t = 0; t < 4; ++t) wb[i][t] = wb[i + 1][t];
+        const float *rec = grec + (j0 + 1 + i) * 8;
+        if ((i + 1) & 1) {
+            step<1>(wb[i], rec, L);
+        } else {
+            step<0>(wb[i], rec, L);
+            transpose_bwd(wb[i], x.next(), L);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LEN; ++i) {
+        float *rec = grec + (j0 + i) * 8;
+        if (i & 1) {
+            ext_step<1, true>(r, wb[i], rec, L, x);
+            transpose_fwd(r, x.next(), L);
+        } else {
+            ext_step<0, true>(r, wb[i], rec, L, x);
+        }
+    }
+}
+
+__device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const float *ck, int j0,
+                                            const Lane &L, Xch &x)
+{
+    float wa[kWin][4];
+    {
+        const float4 c = *reinterpret_cast<const float4 *>(ck);
+        wa[0][0] = c.x; wa[0][1] = c.y; wa[0][2] = c.z; wa[0][3] = c.w;
+    }
+#pragma unroll
+    for (int i = 1; i < kWin; ++i) {       // alpha[j0+i-1] -> alpha[j0+i] uses gamma[j0+i-1]
+#pragma unroll
+        for (int t = 0; t < 4; ++t) wa[i][t] = wa[i - 1][t];
+        const float *rec = grec + (j0 + i - 1) * 8;
+        if ((i - 1) & 1) {
+            step<1>(wa[i], rec, L);
+            transpose_fwd(wa[i], x.next(), L);
+        } else {
+            step<0>(wa[i], rec, L);
+        }
+    }
+#pragma unroll
+    for (int i = kWin - 1; i >= 0; --i) {
+        float *rec = grec + (j0 + i) * 8;
+        if (i & 1) {
+            ext_step<1, false>(wa[i], r, rec, L, x);
+        } else {
+            ext_step<0, false>(wa[i], r, rec, L, x);
+            transpose_bwd(r, x.next(), L);
+        }
+    }
+}
+
+__device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *ckbuf, float *xch,
+                                          int warp, const Lane &L)
+{
+    const int N = g.N, M = g.M;
+    float *grec = gam + L.q * g.rec_stride;
+    float *ckq = ckbuf + L.q * g.ck_stride + 4 * L.p;     // this lane's float4 slot, checkpoint 0
+    Xch x{xch + warp * 2 * kXchFloats, xch + warp * 2 * kXchFloats + kXchFloats};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp == 0) {
+        // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183)
+        for (int k = 0; k < N; k += 2) fwd2(r, grec + k * 8, L, x);
+        // pass 2, first half: checkpoints alpha[0], alpha[8], ...
+        for (int k = 0; k < M; k += 2) {
+            if ((k & (kWin - 1)) == 0)
+                *reinterpret_cast<float4 *>(ckq + (k / kWin) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            fwd2(r, grec + k * 8, L, x);
+        }
+    } else {
+        for (int j = N; j > 0; j -= 2) bwd2(r, grec + (j - 2) * 8, L, x);   // :203-213, :216-217
+        for (int j = N; j > M; j -= 2) {
+            if (j == N || ((j - M) & (kWin - 1)) == 0) {
+                const int w = (j - M + kWin - 1) / kWin - 1;
+                *reinterpret_cast<float4 *>(ckq + (g.nckA + w) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            bwd2(r, grec + (j - 2) * 8, L, x);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 0; w < g.nckB; ++w) {
+            const int j0 = M + w * kWin;
+            const float *ck = ckq + (g.nckA + w) * 16;
+            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, ck, j0, L, x);
+            else                window_alpha<4>(r, grec, ck, j0, L, x);
+        }
+    } else {
+        for (int w = g.nckA - 1; w >= 0; --w)
+            window_beta(r, grec, ckq + w * 16, w * kWin, L, x);
+    }
+    __syncthreads();
+}
+
+// Branch-metric record for one trellis step (dvb_rcs2_turbo.py:131-160): float64
+// left-to-right sums rounded once to float32, then merged per (W,Y) class.
+__device__ __forceinline__ void make_record(float *rec, int k, double YA, double YB, float pW, float pY)
+{
+    const double a = YA * 0.5, b = YB * 0.5;
+    const double w = (double)pW * 0.5, y = (double)pY * 0.5;
+    const double s = __dadd_rn(a, b), d = __dsub_rn(a, b);
+    float P[4], Mv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double sw = (c & 2) ? -w : w, sy = (c & 1) ? -y : y;
+        P[c] = __double2float_rn(__dadd_rn(__dadd_rn(s, sw), sy));
+        Mv[c] = __double2float_rn(__dadd_rn(__dadd_rn(d, sw), sy));
+    }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float GP = fmaxf(P[c], -P[3 - c]);
+        const float GM = fmaxf(Mv[3 - c], -Mv[c]);
+        const bool swap = (k & 1) && (((c >> 1) ^ c) & 1);
+        o[2 * c] = swap ? GM : GP;
+        o[2 * c + 1] = swap ? GP : GM;
+    }
+    *reinterpret_cast<float4 *>(rec) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4 *>(rec + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// Extrinsic epilogue for one step (dvb_rcs2_turbo.py:250-279).
+__device__ __forceinline__ double2 make_extrinsic(const float4 uv, double YA, double YB, double sf)
+{
+    const double a = YA * 0.5, b = YB * 0.5;
+    const bool sP = __dadd_rn(a, b) < 0.0, sM = __dsub_rn(a, b) < 0.0;
+    const float app0 = sP ? uv.y : uv.x, app3 = sP ? uv.x : uv.y;
+    const float app1 = sM ? uv.w : uv.z, app2 = sM ? uv.z : uv.w;
+    const float LA = __fsub_rn(fmaxf(app0, app1), fmaxf(app2, app3));
+    const float LB = __fsub_rn(fmaxf(app0, app2), fmaxf(app1, app3));
+    double ea = __dmul_rn(__dsub_rn((double)LA, YA), sf);
+    double eb = __dmul_rn(__dsub_rn((double)LB, YB), sf);
+    ea = ea > 300.0 ? 300.0 : ea; ea = ea < -300.0 ? -300.0 : ea;
+    eb = eb > 300.0 ? 300.0 : eb; eb = eb < -300.0 ? -300.0 : eb;
+    return make_double2(ea, eb);
+}
+
+template <bool SISO_ONLY>
+__global__ void __launch_bounds__(kCtaThreads)
+quad_kernel(const QuadArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QuadGeom g = A.g;
+    const int N = g.N;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- shared memory carve-up -------------------------------------------------
+    int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
+    const int tab_bytes = ((7 * N * 2 + 15) / 16) * 16;
+    float *gam = reinterpret_cast<float *>(smem_raw + tab_bytes);
+    float *ckbuf = gam + kFramesPerCta * g.rec_stride;
+    float *xch = ckbuf + kFramesPerCta * g.ck_stride;
+    int *flags = reinterpret_cast<int *>(xch + 4 * kXchFloats);
+    unsigned char *hb = reinterpret_cast<unsigned char *>(flags + 16);   // [8][N] hard-bit pairs
+
+    for (int i = tid; i < 7 * N; i += kCtaThreads) tab[i] = A.tab[i];
+    const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
+
+    Lane L;
+    L.q = lane >> 2; L.p = lane & 3;
+    L.oA[0] = cls2(L.p);     L.oB[0] = cls2(L.p + 4);
+    L.oA[1] = cls2(2 * L.p); L.oB[1] = cls2(2 * L.p + 1);
+    L.xw = xbase(L.q) + 4 * L.p;
+    L.xr = xbase(L.q) + L.p;
+    L.role_word = ((L.p & 1) << 1) | (L.p >> 1);      // roles (U0,V1,U3,V2) -> words (0,2,1,3)
+
+    unsigned long long bit_err = 0, frm_err = 0, frames_done = 0;
+    const size_t slot0 = (size_t)blockIdx.x * kFramesPerCta * N;
+    double2 *Le1 = A.Le1 + slot0, *Le2 = A.Le2 + slot0, *Yb = A.Y + slot0;
+
+    for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
+        const long long frame0 = (long long)grp * kFramesPerCta;
+        const int n_half = SISO_ONLY ? 1 : 2 * A.iterations;
+        for (int h = 0; h < n_half; ++h) {
+            const int second = h & 1;                      // 0: SISO1 (natural), 1: SISO2 (interleaved)
+            const bool first = (h == 0);
+            const double sf = SISO_ONLY ? A.siso_sf
+                                        : ((h >> 1) < A.iterations - 1 ? A.sf_inner : A.sf_last);
+            const double2 *LePrev = second ? Le1 : Le2;
+            double2 *LeOut = second ? Le2 : Le1;
+            const int16_t *t_oW = tab + (3 + 2 * second) * N, *t_oY = tab + (4 + 2 * second) * N;
+            __syncthreads();   // tables loaded / previous phase finished with gam, Le
+            // ---- prep: gather, a-priori add, branch-metric records ------------------
+            for (int f = 0; f < kFramesPerCta; ++f) {
+                const long long frame = frame0 + f;
+                const bool valid = frame < A.B;
+                float *grec = gam + f * g.rec_stride;
+                for (int k = tid; k < N; k += kCtaThreads) {
+                    float sA = 0.f, sB = 0.f, pW = 0.f, pY = 0.f;
+                    double2 La = make_double2(0.0, 0.0);
+                    if (valid) {
+                        if (SISO_ONLY) {
+                            const size_t i = (size_t)frame * N + k;
+                            sA = __ldg(A.LcA + i); sB = __ldg(A.LcB + i);
+                            pW = __ldg(A.LcW + i); pY = __ldg(A.LcY + i);
+                            if (A.LaA) La.x = __ldg(A.LaA + i);
+                            if (A.LaB) La.y = __ldg(A.LaB + i);
+                        } else {
+                            const float *Lf = A.llr + frame * A.llr_stride;
+                            const int src = second ? t_perm[k] : k;
+                            const int oa = t_offA[src];
+                            sA = __ldg(Lf + oa); sB = __ldg(Lf + oa + 1);
+                            const int ow = t_oW[k], oy = t_oY[k];
+                            if (ow >= 0) pW = __ldg(Lf + ow);
+                            if (oy >= 0) pY = __ldg(Lf + oy);
+                            if (!first) La = __ldcg(LePrev + (size_t)f * N + (second ? src : (int)t_inv[k]));
+                        }
+                    }
+                    const double YA = __dadd_rn((double)sA, La.x);   // Lc_A[k] + La_A[k] (:135)
+                    const double YB = __dadd_rn((double)sB, La.y);
+                    make_record(grec + k * 8, k, YA, YB, pW, pY);
+                    __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
+                }
+            }
+            __syncthreads();
+            siso_core(g, gam, ckbuf, xch, warp, L);
+            // ---- epilogue: extrinsic LLRs (float64) ---------------------------------
+            for (int f = 0; f < kFramesPerCta; ++f) {
+                const long long frame = frame0 + f;
+                if (frame >= A.B) break;
+                const float *grec = gam + f * g.rec_stride;
+                for (int k = tid; k < N; k += kCtaThreads) {
+                    const float4 uv = *reinterpret_cast<const float4 *>(grec + k * 8);
+                    const double2 Y = __ldcg(Yb + (size_t)f * N + k);
+                    const double2 e = make_extrinsic(uv, Y.x, Y.y, sf);
+                    if (SISO_ONLY) {
+                        A.LeA[(size_t)frame * N + k] = e.x;
+                        A.LeB[(size_t)frame * N + k] = e.y;
+                    } else {
+                        __stcg(LeOut + (size_t)f * N + k, e);
+                    }
+                }
+            }
+        }
+        if (SISO_ONLY) continue;
+        __syncthreads();
+        // ---- hard decision (dvb_rcs2_turbo.py:526-537) + optional error counting ----
+        if (tid < kFramesPerCta) flags[tid] = 0;
+        __syncthreads();
+        for (int f = 0; f < kFramesPerCta; ++f) {
+            const long long frame = frame0 + f;
+            if (frame >= A.B) break;
+            const float *Lf = A.llr + frame * A.llr_stride;
+            int errs = 0;
+            for (int j = tid; j < N; j += kCtaThreads) {
+                const int oa = t_offA[j];
+                const double2 La = __ldcg(Le2 + (size_t)f * N + t_inv[j]);
+                const double2 e1 = __ldcg(Le1 + (size_t)f * N + j);
+                const double LA = __dadd_rn(__dadd_rn((double)__ldg(Lf + oa), La.x), e1.x);
+                const double LB = __dadd_rn(__dadd_rn((double)__ldg(Lf + oa + 1), La.y), e1.y);
+                const int bA = LA < 0.0, bB = LB < 0.0;
+                if (A.bits)
+                    *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * j) = make_int2(bA, bB);
+                hb[f * N + j] = (unsigned char)(bA | (bB << 1));
+                if (A.ref_bits) {
+                    const uchar2 rb = *reinterpret_cast<const uchar2 *>(A.ref_bits + (size_t)frame * 2 * N + 2 * j);
+                    errs += (bA != rb.x) + (bB != rb.y);
+                }
+            }
+            if (A.ref_bits) {
+                bit_err += errs;
+                if (errs) atomicOr(&flags[f], 1);
+            }
+        }
+        __syncthreads();
+        if (A.packed) {
+            const int wpf = (2 * N + 31) / 32;
+            for (int i = tid; i < kFramesPerCta * wpf; i += kCtaThreads) {
+                const int f = i / wpf, w = i - f * wpf;
+                if (frame0 + f >= A.B) continue;
+                unsigned v = 0;
+                for (int t = 0; t < 16; ++t) {
+                    const int j = w * 16 + t;
+                    if (j < N) v |= (unsigned)hb[f * N + j] << (2 * t);
+                }
+                A.packed[(size_t)(frame0 + f) * wpf + w] = v;
+            }
+        }
+        if (tid < kFramesPerCta && frame0 + tid < A.B) {
+            frames_done += 1;
+            frm_err += flags[tid];
+        }
+    }
+    if (!SISO_ONLY && A.counters) {
+        // one atomic per warp and counter at kernel end
+        for (int o = 16; o > 0; o >>= 1) {
+            bit_err += __shfl_xor_sync(0xffffffffu, bit_err, o);
+            frm_err += __shfl_xor_sync(0xffffffffu, frm_err, o);
+            frames_done += __shfl_xor_sync(0xffffffffu, frames_done, o);
+        }
+        if (lane == 0) {
+            if (bit_err) atomicAdd(A.counters + 0, bit_err);
+            if (frm_err) atomicAdd(A.counters + 1, frm_err);
+            if (frames_done) {
+                atomicAdd(A.counters + 2, frames_done);
+                atomicAdd(A.counters + 3, frames_done * 2ull * N);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static size_t quad_smem_bytes(const QuadGeom &g)
+{
+    size_t tab = ((size_t)7 * g.N * 2 + 15) / 16 * 16;
+    size_t fl = (size_t)kFramesPerCta * g.rec_stride + (size_t)kFramesPerCta * g.ck_stride + 4 * kXchFloats;
+    return tab + fl * 4 + 16 * 4 + (size_t)kFramesPerCta * g.N;
+}
+
+int quad_configure(Codec &c)
+{
+    QuadGeom &g = c.geom;
+    const int N = c.N;
+    if (N < 8 || N > kMaxN || (N % 4) != 0) return B200DVB_ENOSPEC;
+    g.N = N;
+    g.M = ((N / 2) / kWin) * kWin;
+    if (g.M == 0) g.M = kWin <= N - 4 ? kWin : 0;
+    if (g.M <= 0 || g.M >= N) return B200DVB_ENOSPEC;
+    g.nckA = g.M / kWin;
+    g.nckB = (N - g.M + kWin - 1) / kWin;
+    g.rec_stride = 8 * N + 8;                       // == 8 (mod 32): 4 frames tile the 32 banks
+    int ck = (g.nckA + g.nckB) * 16;
+    if ((ck % 32) == 0) ck += 16;                   // == 16 (mod 32)
+    g.ck_stride = ck;
+    g.frames = kFramesPerCta;
+    g.smem_bytes = quad_smem_bytes(g);
+    int dev = 0;
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaGetDeviceProperties(&prop, dev));
+    c.num_sms = prop.multiProcessorCount;
+    if (g.smem_bytes > (size_t)prop.sharedMemPerBlockOptin) return B200DVB_ENOSPEC;
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    int occ = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false>, kCtaThreads, g.smem_bytes));
+    if (occ < 1) return B200DVB_ENOSPEC;
+    g.ctas_per_sm = occ;
+    return B200DVB_OK;
+}
+
+static int grid_for(const Codec &c, int B)
+{
+    const int groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    const int cap = c.num_sms * c.geom.ctas_per_sm;
+    return groups < cap ? groups : cap;
+}
+
+size_t decode_workspace_bytes(const Codec &c, int B)
+{
+    return (size_t)3 * grid_for(c, B) * kFramesPerCta * c.N * sizeof(double2) + 256;
+}
+size_t siso_workspace_bytes(const Codec &c, int B)
+{
+    return (size_t)grid_for(c, B) * kFramesPerCta * c.N * sizeof(double2) + 256;
+}
+
+static inline unsigned char *align256(void *p)
+{
+    return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
+}
+
+int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
+                  uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,
+                  void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    if (ws_bytes < decode_workspace_bytes(c, B)) return B200DVB_ENOMEM;
+    const int grid = grid_for(c, B);
+    const size_t per = (size_t)grid * kFramesPerCta * c.N;
+    QuadArgs A{};
+    A.g = c.geom; A.B = B; A.iterations = c.iterations;
+    A.n_groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
+    A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
+    A.ref_bits = ref_bits; A.counters = counters;
+    A.Le1 = reinterpret_cast<double2 *>(align256(ws));
+    A.Le2 = A.Le1 + per; A.Y = A.Le2 + per;
+    quad_kernel<false><<<grid, kCtaThreads, c.geom.smem_bytes, s>>>(A);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, const float *Lc_W,
+                const float *Lc_Y, const double *La_A, const double *La_B, double sf,
+                double *Le_A, double *Le_B, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    if (ws_bytes < siso_workspace_bytes(c, B)) return B200DVB_ENOMEM;
+    const int grid = grid_for(c, B);
+    QuadArgs A{};
+    A.g = c.geom; A.B = B; A.iterations = 1;
+    A.n_groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    A.tab = c.d_tab;
+    A.LcA = Lc_A; A.LcB = Lc_B; A.LcW = Lc_W; A.LcY = Lc_Y; A.LaA = La_A; A.LaB = La_B;
+    A.LeA = Le_A; A.LeB = Le_B; A.siso_sf = sf;
+    A.Y = reinterpret_cast<double2 *>(align256(ws));
+    A.Le1 = A.Y; A.Le2 = A.Y;
+    quad_kernel<true><<<grid, kCtaThreads, c.geom.smem_bytes, s>>>(A);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+}  // namespace b200dvb

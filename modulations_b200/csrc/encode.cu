@@ -1,0 +1,193 @@
+// encode.cu — tail-biting duo-binary encoder + on-device Monte-Carlo source.
+//
+// Reference: DVBRCS2_Turbo.encode / _encode_component (dvb_rcs2_turbo.py:404-462)
+// and the GF(2) circular-state solve (dvb_rcs2_turbo.py:50-114).  The solve
+// Sc = (I + G^N)^-1 Z is linear over GF(2) in a 4-bit state, so for a given N it
+// is a 16-entry nibble table; the host packs it into one 64-bit word
+// (api.cu: circular_lut) and the kernel does `lut >> (4*Z) & 15`.
+//
+// Layout: a block stages `fpb` frames in shared memory (coalesced 16-byte
+// copies in and out); one thread walks one frame's trellis four times (zero-state
+// pass + circular pass for each constituent encoder).  Rows are padded to an odd
+// number of 32-bit words so the 32 walking threads hit 32 different banks.
+#include "common.cuh"
+
+namespace b200dvb {
+
+namespace {
+
+__device__ __forceinline__ int trellis_next(int s, int ab)
+{   // dk = A^B^s2^s3 ; ns = (s2,s1,s0,dk)   (dvb_rcs2_turbo.py:351,366)
+    return ((s & 7) << 1) | (ab ^ ((s >> 2) & 1) ^ ((s >> 3) & 1));
+}
+
+__global__ void encode_kernel(int B, int N, int n_llr, int fpb, int in_stride, int out_stride,
+                              const int16_t *__restrict__ tab, unsigned long long lut,
+                              const uint8_t *__restrict__ info, uint8_t *__restrict__ coded,
+                              uint8_t *__restrict__ circ)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned char *s_in = sm;                               // [fpb][in_stride]
+    unsigned char *s_out = sm + (size_t)fpb * in_stride;    // [fpb][out_stride]
+    const int f0 = blockIdx.x * fpb;
+    const int nf = min(fpb, B - f0);
+    const int k2 = 2 * N;
+    // stage info bits (byte granular: rows of 2N bytes need not be 16-byte aligned)
+    for (int i = threadIdx.x; i < nf * k2; i += blockDim.x) {
+        const int f = i / k2, j = i - f * k2;
+        s_in[f * in_stride + j] = info[(size_t)(f0 + f) * k2 + j] & 1;
+    }
+    __syncthreads();
+    if (threadIdx.x < nf) {
+        const unsigned char *in = s_in + threadIdx.x * in_stride;
+        unsigned char *out = s_out + threadIdx.x * out_stride;
+        const int16_t *perm = tab, *offA = tab + 2 * N;
+        for (int e = 0; e < 2; ++e) {
+            const int16_t *oW = tab + (3 + 2 * e) * N, *oY = tab + (4 + 2 * e) * N;
+            int st = 0;                                     // zero-state response (:408-412)
+            for (int i = 0; i < N; ++i) {
+                const int j = e ? perm[i] : i;
+                st = trellis_next(st, in[2 * j] ^ in[2 * j + 1]);
+            }
+            st = (int)((lut >> (4 * st)) & 15ull);          // circular start state (:416-417)
+            if (circ) circ[(size_t)(f0 + threadIdx.x) * 2 + e] = (uint8_t)st;
+            for (int i = 0; i < N; ++i) {                   // :423-427
+                const int j = e ? perm[i] : i;
+                const int a = in[2 * j], b = in[2 * j + 1], ab = a ^ b;
+                const int s0 = st & 1, s1 = (st >> 1) & 1, s2 = (st >> 2) & 1;
+                if (e == 0) { const int oa = offA[i]; out[oa] = a; out[oa + 1] = b; }
+                const int ow = oW[i], oy = oY[i];
+                if (ow >= 0) out[ow] = ab ^ s0 ^ s1 ^ s2;   // :355
+                if (oy >= 0) out[oy] = ab ^ s1;             // :359
+                st = trellis_next(st, ab);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf * n_llr; i += blockDim.x) {
+        const int f = i / n_llr, j = i - f * n_llr;
+        coded[(size_t)(f0 + f) * n_llr + j] = s_out[f * out_stride + j];
+    }
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ------------------------
+struct Philox { unsigned c[4]; };
+__device__ __forceinline__ Philox philox(unsigned long long counter, unsigned stream,
+                                         unsigned long long seed)
+{
+    unsigned c0 = (unsigned)counter, c1 = (unsigned)(counter >> 32), c2 = stream, c3 = 0x5eed5eedu;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox{{c0, c1, c2, c3}};
+}
+
+__global__ void info_bits_kernel(size_t n16, unsigned long long seed, unsigned long long offset16,
+                                 uint4 *__restrict__ out)
+{   // 16 info bits (as 16 bytes) per thread
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const Philox r = philox(offset16 + i, 1u, seed);
+    const unsigned v = r.c[0];
+    uint4 o;
+    o.x = (v & 1u) | ((v >> 1 & 1u) << 8) | ((v >> 2 & 1u) << 16) | ((v >> 3 & 1u) << 24);
+    o.y = (v >> 4 & 1u) | ((v >> 5 & 1u) << 8) | ((v >> 6 & 1u) << 16) | ((v >> 7 & 1u) << 24);
+    o.z = (v >> 8 & 1u) | ((v >> 9 & 1u) << 8) | ((v >> 10 & 1u) << 16) | ((v >> 11 & 1u) << 24);
+    o.w = (v >> 12 & 1u) | ((v >> 13 & 1u) << 8) | ((v >> 14 & 1u) << 16) | ((v >> 15 & 1u) << 24);
+    out[i] = o;
+}
+
+// BPSK 0 -> +1 over AWGN, llr = 2y/sigma^2 clipped to +-50 (turbo_test_suite.py:147-161).
+// Reads coded bytes, writes float LLRs; 4 elements per thread (one Philox call ->
+// two Box-Muller pairs).
+__global__ void awgn_bpsk_kernel(size_t n4, size_t n, float sigma, float two_over_var,
+                                 unsigned long long seed, unsigned long long offset4,
+                                 const uint8_t *__restrict__ coded, float *__restrict__ llr)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const Philox r = philox(offset4 + i, 2u, seed);
+    float nrm[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)r.c[2 * h] + 0.5f) * 2.3283064365386963e-10f;
+        const float u2 = ((float)r.c[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
+        const float rad = sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        nrm[2 * h] = rad * cs; nrm[2 * h + 1] = rad * sn;
+    }
+    const size_t e = 4 * i;
+    if (e + 3 < n) {
+        const uchar4 c = *reinterpret_cast<const uchar4 *>(coded + e);
+        float4 o;
+        o.x = fminf(fmaxf(((1.f - 2.f * c.x) + sigma * nrm[0]) * two_over_var, -50.f), 50.f);
+        o.y = fminf(fmaxf(((1.f - 2.f * c.y) + sigma * nrm[1]) * two_over_var, -50.f), 50.f);
+        o.z = fminf(fmaxf(((1.f - 2.f * c.z) + sigma * nrm[2]) * two_over_var, -50.f), 50.f);
+        o.w = fminf(fmaxf(((1.f - 2.f * c.w) + sigma * nrm[3]) * two_over_var, -50.f), 50.f);
+        *reinterpret_cast<float4 *>(llr + e) = o;
+    } else {
+        for (int t = 0; t < 4 && e + t < n; ++t)
+            llr[e + t] = fminf(fmaxf(((1.f - 2.f * coded[e + t]) + sigma * nrm[t]) * two_over_var, -50.f), 50.f);
+    }
+}
+
+int odd_words(int bytes)
+{
+    int w = (bytes + 3) / 4;
+    if ((w & 1) == 0) ++w;
+    return w * 4;
+}
+
+}  // namespace
+
+int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,
+                  cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    const int in_stride = odd_words(2 * c.N), out_stride = odd_words(c.n_llr);
+    int fpb = 32;
+    while (fpb > 1 && (size_t)fpb * (in_stride + out_stride) > 96 * 1024) fpb >>= 1;
+    const size_t smem = (size_t)fpb * (in_stride + out_stride);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    unsigned long long lut = 0;
+    for (int z = 0; z < 16; ++z) lut |= (unsigned long long)(c.circ_lut[z] & 15) << (4 * z);
+    const int grid = (B + fpb - 1) / fpb;
+    encode_kernel<<<grid, 128, smem, s>>>(B, c.N, c.n_llr, fpb, in_stride, out_stride, c.d_tab, lut,
+                                          info, coded, circ);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+int launch_mc_bpsk(const Codec &c, int B, float noise_var, unsigned long long seed,
+                   unsigned long long frame_offset, uint8_t *info, uint8_t *coded, float *llr,
+                   cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    const size_t nbits = (size_t)B * 2 * c.N;
+    if ((nbits % 16) != 0) return B200DVB_ENOSPEC;          // whole 16-bit Philox draws only
+    const size_t n16 = nbits / 16;
+    const unsigned long long off16 = frame_offset * (unsigned long long)(2 * c.N) / 16ull;
+    info_bits_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(n16, seed, off16,
+                                                                   reinterpret_cast<uint4 *>(info));
+    B2_CUDA(cudaGetLastError());
+    int rc = launch_encode(c, B, info, coded, nullptr, s);
+    if (rc != B200DVB_OK) return rc;
+    const size_t n = (size_t)B * c.n_llr, n4 = (n + 3) / 4;
+    awgn_bpsk_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
+        n4, n, sqrtf(noise_var), 2.0f / noise_var, seed,
+        frame_offset * (unsigned long long)c.n_llr / 4ull, coded, llr);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+}  // namespace b200dvb

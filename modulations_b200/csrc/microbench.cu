@@ -1,0 +1,102 @@
+// microbench.cu — measured issue rates of the instructions the decoder is made of
+// (lane-ops per clock per SM).  bench.py quotes the ALU roofline against the
+// nominal 64 ACS/clk/SM of SURVEY §8(d) AND against these measured pipes.
+//
+// results[0] FADD   results[1] FMNMX   results[2] ACS mix (2 FADD + 1 FMNMX)
+// results[3] SHFL   results[4] DADD    results[5] F2F.F32.F64
+// results[6] add.f32x2 (counted as 2 lane-ops)   results[7] SM clock in MHz
+#include "common.cuh"
+
+namespace b200dvb {
+
+namespace {
+
+constexpr int kIter = 4096;
+constexpr int kChains = 8;
+
+template <int OP>
+__global__ void __launch_bounds__(1024) probe(float seed, long long *cycles, float *sink)
+{
+    float x[kChains];
+    double d[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) { x[i] = seed + i + threadIdx.x; d[i] = x[i]; }
+    const float c = seed * 0.5f, c2 = seed * 0.25f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < kIter; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            if (OP == 0) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(c));
+            if (OP == 1) asm volatile("max.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(c));
+            if (OP == 2) {
+                float a, b;
+                asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(a) : "f"(x[i]), "f"(c));
+                asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(b) : "f"(x[(i + 1) % kChains]), "f"(c2));
+                asm volatile("max.f32 %0, %1, %2;" : "=f"(x[i]) : "f"(a), "f"(b));
+            }
+            if (OP == 3) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+f"(x[i]));
+            if (OP == 4) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"((double)c));
+            if (OP == 5) asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(x[i]) : "d"(d[i]));
+            if (OP == 6) {
+                unsigned long long p, q;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x[i]), "f"(x[(i + 1) % kChains]));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(q) : "f"(c));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(q));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x[i]), "=f"(x[(i + 1) % kChains]) : "l"(p));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) acc += x[i] + (float)d[i];
+    if (acc == 123.456f) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+int run_one(int sms, long long *d_cycles, float *d_sink, double ops_per_iter, double *out)
+{
+    probe<OP><<<sms, 1024>>>(1.0f, d_cycles, d_sink);   // warm-up
+    probe<OP><<<sms, 1024>>>(1.0f, d_cycles, d_sink);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaDeviceSynchronize());
+    long long *h = (long long *)malloc(sizeof(long long) * sms);
+    B2_CUDA(cudaMemcpy(h, d_cycles, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < sms; ++i) avg += (double)h[i];
+    avg /= sms;
+    free(h);
+    *out = 1024.0 * kIter * kChains * ops_per_iter / avg;
+    return B200DVB_OK;
+}
+
+}  // namespace
+
+int run_microbench(double *r)
+{
+    int dev = 0, sms = 0, khz = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B2_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    long long *d_cycles = nullptr;
+    float *d_sink = nullptr;
+    B2_CUDA(cudaMalloc(&d_cycles, sizeof(long long) * sms));
+    B2_CUDA(cudaMalloc(&d_sink, sizeof(float)));
+    int rc = B200DVB_OK;
+    if (rc == 0) rc = run_one<0>(sms, d_cycles, d_sink, 1, r + 0);
+    if (rc == 0) rc = run_one<1>(sms, d_cycles, d_sink, 1, r + 1);
+    if (rc == 0) rc = run_one<2>(sms, d_cycles, d_sink, 1, r + 2);   // one ACS per iteration
+    if (rc == 0) rc = run_one<3>(sms, d_cycles, d_sink, 1, r + 3);
+    if (rc == 0) rc = run_one<4>(sms, d_cycles, d_sink, 1, r + 4);
+    if (rc == 0) rc = run_one<5>(sms, d_cycles, d_sink, 1, r + 5);
+    if (rc == 0) rc = run_one<6>(sms, d_cycles, d_sink, 2, r + 6);
+    r[7] = khz / 1000.0;
+    cudaFree(d_cycles);
+    cudaFree(d_sink);
+    return rc;
+}
+
+}  // namespace b200dvb

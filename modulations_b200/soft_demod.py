@@ -1,0 +1,32 @@
+"""Drop-in for ``compute_llr`` (reference ``test_sdr_with_coding.py:200-225``):
+max-log bit LLRs over a constellation enumerated from the mapper, sigma^2 floored
+at 0.005, clipped to +-30, positive = bit 1.  Extended to 64QAM and
+256QAM over the ``SDRModem`` constellations (the reference stops at 16QAM).
+
+Runs in float32 on the GPU (``b200dvb_demap``); the reference computes in float64,
+so results agree to a stated absolute tolerance (tests/test_gpu_modem.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .sdr_modem import gray_modem, ModemHandle
+
+
+def compute_llr(syms, mod_type, noise_var, constellation=None):
+    """-> float64[n*bps] (numpy in) or float32 CUDA tensor (torch in)."""
+    if mod_type not in _lib.MOD_IDS:
+        raise KeyError(mod_type)                         # reference: MODULATIONS[mod_type] KeyError
+    modem = gray_modem(mod_type) if constellation is None else ModemHandle(mod_type, constellation)
+    torch = _lib.torch_mod()
+    out = modem.llr(syms, noise_var)
+    if isinstance(out, torch.Tensor):
+        return out
+    return out.astype(np.float64)
+
+
+def decoder_llr(syms, mod_type, noise_var):
+    """LLRs in the DECODER's convention (positive = bit 0): -compute_llr, fused in
+    the kernel as scale = -1."""
+    return gray_modem(mod_type).llr(syms, noise_var, scale=-1.0)

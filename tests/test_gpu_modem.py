@@ -1,0 +1,116 @@
+"""GPU parity tests for mapper / slicer / soft demapper vs oracle/ and golden."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import vectors
+
+pytestmark = pytest.mark.gpu
+
+# float32 kernel vs the reference's float64: |d0 - d1| carries ~1e-6 absolute error
+# for unit-power constellations, divided by the noise variance.
+def llr_atol(nv):
+    return 4e-6 / max(nv, 0.005) + 2e-6
+
+
+@pytest.mark.parametrize("name", list(vectors.BPS))
+def test_mapper_and_slicer(golden, name):
+    from modulations_b200.sdr_modem import SDRModem
+    m = golden["modem_kat"]
+    sm = SDRModem()
+    bits = vectors.mapper_bits(name)
+    syms = sm.modulate(bits, name)
+    assert syms.dtype == m[f"{name}/syms"].dtype
+    assert np.array_equal(syms, m[f"{name}/syms"])                       # bit-exact mapping
+    rx = vectors.noisy_symbols(syms, name)
+    hard = sm.demodulate(rx, name)
+    assert np.array_equal(hard, m[f"{name}/hard"])
+    assert np.array_equal(sm.demodulate(rx.astype(np.complex64), name),
+                          oracle.demodulate(rx.astype(np.complex64), name))
+
+
+@pytest.mark.parametrize("name", ['BPSK', 'QPSK', '8PSK', '16QAM', '64QAM'])
+def test_modulator_alt_tables(golden, name):
+    from modulations_b200.modulators import Modulator
+    m = golden["modem_kat"]
+    mo = Modulator()
+    fn = getattr(mo, "mod_" + name.lower())
+    dfn = getattr(mo, "demod_" + name.lower())
+    bits = vectors.mapper_bits(name)
+    syms = fn(bits)
+    assert np.array_equal(syms, m[f"alt_{name}/syms"])
+    rx = vectors.noisy_symbols(syms, name)
+    assert np.array_equal(dfn(rx), m[f"alt_{name}/hard"])
+
+
+@pytest.mark.parametrize("name", list(vectors.BPS))
+def test_compute_llr(golden, name):
+    from modulations_b200.soft_demod import compute_llr, decoder_llr
+    m = golden["modem_kat"]
+    rx = vectors.noisy_symbols(oracle.modulate(vectors.mapper_bits(name), name), name)
+    for nv in vectors.DEMAP_NOISE_VARS + [0.0001]:
+        got = compute_llr(rx, name, nv)
+        assert got.dtype == np.float64 and got.shape == (len(rx) * vectors.BPS[name],)
+        want = oracle.compute_llr(rx, name, nv)
+        key = f"{name}/llr_nv{nv}"
+        if key in m.files:                                               # reference's own output
+            assert np.array_equal(want[:vectors.DEMAP_N * vectors.BPS[name]], m[key])
+        err = np.abs(got - want)
+        assert err.max() <= llr_atol(nv), (name, nv, err.max())
+        # identical hard decisions except on near-zero |LLR| ties
+        bad = (got > 0) != (want > 0)
+        assert np.all(np.abs(want[bad]) < llr_atol(nv))
+        assert np.array_equal(decoder_llr(rx, name, nv), -got.astype(np.float32))
+    assert np.all(np.abs(compute_llr(rx, name, 0.001)) <= 30.0)
+
+
+@pytest.mark.parametrize("name", ['QPSK', '16QAM', '64QAM', '256QAM'])
+def test_generic_and_separable_kernels_agree(name):
+    """The piecewise-linear per-axis kernel and the brute-force table kernel are two
+    implementations of the same max-log rule."""
+    from modulations_b200.sdr_modem import ModemHandle, gray_constellation
+    rx = vectors.noisy_symbols(oracle.modulate(vectors.mapper_bits(name), name), name)
+    table = gray_constellation(name)
+    fast = ModemHandle(name, table)
+    # rotating the table by a hair breaks separability -> generic kernel
+    rot = np.exp(1j * 1e-9)
+    slow = ModemHandle(name, table.astype(np.complex128) * rot)
+    a, b = fast.llr(rx, 0.05), slow.llr(rx, 0.05)
+    assert np.abs(a - b).max() < 2e-4
+
+
+def test_modulator_llr_nongray_table():
+    """compute_llr over a caller-supplied (non-Gray) table."""
+    from modulations_b200.modulators import natural_constellation
+    from modulations_b200.soft_demod import compute_llr
+    c = natural_constellation('16QAM')
+    rs = np.random.RandomState(2)
+    bits = rs.randint(0, 2, 4 * 500)
+    rx = oracle.modulator_mod(bits, '16QAM') + 0.1 * (rs.randn(500) + 1j * rs.randn(500))
+    got = compute_llr(rx, '16QAM', 0.02, constellation=c)
+    want = oracle.compute_llr(rx, '16QAM', 0.02, constellation=c)
+    assert np.abs(got - want).max() <= llr_atol(0.02)
+
+
+def test_coded_16qam_pipeline(golden):
+    """Config 3 shape: encode -> 16QAM map -> AWGN -> demap (sign flipped, F4) ->
+    pad/trim to n_coded (test_sdr_with_coding.py:474-478) -> decode; the GPU chain
+    must give the oracle chain's bits when fed the oracle's float32 LLRs, and its
+    own LLRs must agree within tolerance."""
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    from modulations_b200.sdr_modem import SDRModem
+    from modulations_b200.soft_demod import decoder_llr
+    N, rate = 212, '1/2'
+    g = turbo.DVBRCS2_Turbo(N, rate, 8)
+    o = oracle.OracleTurbo(N, rate, 8, perm=g.perm, inv_perm=g.inv_perm)
+    rs = np.random.RandomState(8)
+    info = rs.randint(0, 2, 2 * N)
+    coded = g.encode(info)
+    syms = SDRModem().modulate(coded, '16QAM')
+    assert np.array_equal(syms, oracle.modulate(coded, '16QAM'))
+    nv = 1.0 / (4 * 0.5 * 10 ** 0.6)
+    rx = syms + np.sqrt(nv / 2) * (rs.randn(len(syms)) + 1j * rs.randn(len(syms)))
+    llr_o = (-oracle.compute_llr(rx, '16QAM', nv))[:g.n_coded].astype(np.float32)
+    llr_g = decoder_llr(rx, '16QAM', nv)[:g.n_coded]
+    assert np.abs(llr_g - llr_o).max() <= llr_atol(nv)
+    assert np.array_equal(g.decode(llr_o), o.decode(llr_o))

@@ -351,8 +351,10 @@ quad_kernel(const QuadArgs A)
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((7 * N * 2 + 15) / 16) * 16;
     float *gam = reinterpret_cast<float *>(smem_raw + tab_bytes);
-    float *ckbuf = gam + kFramesPerCta * g.rec_stride;
-    float *xch = ckbuf + kFramesPerCta * g.ck_stride;
+    const int FR = g.frames;                         // frames this CTA decodes at a time
+    const int areas = FR + (FR < kFramesPerCta);     // idle quads (q >= FR) share one scratch area
+    float *ckbuf = gam + areas * g.rec_stride;
+    float *xch = ckbuf + areas * g.ck_stride;
     int *flags = reinterpret_cast<int *>(xch + 4 * kXchFloats);
     unsigned char *hb = reinterpret_cast<unsigned char *>(flags + 16);   // [8][N] hard-bit pairs
 
@@ -360,19 +362,19 @@ quad_kernel(const QuadArgs A)
     const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
 
     Lane L;
-    L.q = lane >> 2; L.p = lane & 3;
+    L.q = min(lane >> 2, FR); L.p = lane & 3;
     L.oA[0] = cls2(L.p);     L.oB[0] = cls2(L.p + 4);
     L.oA[1] = cls2(2 * L.p); L.oB[1] = cls2(2 * L.p + 1);
-    L.xw = xbase(L.q) + 4 * L.p;
-    L.xr = xbase(L.q) + L.p;
+    L.xw = xbase(lane >> 2) + 4 * L.p;
+    L.xr = xbase(lane >> 2) + L.p;
     L.role_word = ((L.p & 1) << 1) | (L.p >> 1);      // roles (U0,V1,U3,V2) -> words (0,2,1,3)
 
     unsigned long long bit_err = 0, frm_err = 0, frames_done = 0;
-    const size_t slot0 = (size_t)blockIdx.x * kFramesPerCta * N;
+    const size_t slot0 = (size_t)blockIdx.x * FR * N;
     double2 *Le1 = A.Le1 + slot0, *Le2 = A.Le2 + slot0, *Yb = A.Y + slot0;
 
     for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
-        const long long frame0 = (long long)grp * kFramesPerCta;
+        const long long frame0 = (long long)grp * FR;
         const int n_half = SISO_ONLY ? 1 : 2 * A.iterations;
         for (int h = 0; h < n_half; ++h) {
             const int second = h & 1;                      // 0: SISO1 (natural), 1: SISO2 (interleaved)
@@ -384,7 +386,7 @@ quad_kernel(const QuadArgs A)
             const int16_t *t_oW = tab + (3 + 2 * second) * N, *t_oY = tab + (4 + 2 * second) * N;
             __syncthreads();   // tables loaded / previous phase finished with gam, Le
             // ---- prep: gather, a-priori add, branch-metric records ------------------
-            for (int f = 0; f < kFramesPerCta; ++f) {
+            for (int f = 0; f < FR; ++f) {
                 const long long frame = frame0 + f;
                 const bool valid = frame < A.B;
                 float *grec = gam + f * g.rec_stride;
@@ -418,7 +420,7 @@ quad_kernel(const QuadArgs A)
             __syncthreads();
             siso_core(g, gam, ckbuf, xch, warp, L);
             // ---- epilogue: extrinsic LLRs (float64) ---------------------------------
-            for (int f = 0; f < kFramesPerCta; ++f) {
+            for (int f = 0; f < FR; ++f) {
                 const long long frame = frame0 + f;
                 if (frame >= A.B) break;
                 const float *grec = gam + f * g.rec_stride;
@@ -438,9 +440,9 @@ quad_kernel(const QuadArgs A)
         if (SISO_ONLY) continue;
         __syncthreads();
         // ---- hard decision (dvb_rcs2_turbo.py:526-537) + optional error counting ----
-        if (tid < kFramesPerCta) flags[tid] = 0;
+        if (tid < FR) flags[tid] = 0;
         __syncthreads();
-        for (int f = 0; f < kFramesPerCta; ++f) {
+        for (int f = 0; f < FR; ++f) {
             const long long frame = frame0 + f;
             if (frame >= A.B) break;
             const float *Lf = A.llr + frame * A.llr_stride;
@@ -468,7 +470,7 @@ quad_kernel(const QuadArgs A)
         __syncthreads();
         if (A.packed) {
             const int wpf = (2 * N + 31) / 32;
-            for (int i = tid; i < kFramesPerCta * wpf; i += kCtaThreads) {
+            for (int i = tid; i < FR * wpf; i += kCtaThreads) {
                 const int f = i / wpf, w = i - f * wpf;
                 if (frame0 + f >= A.B) continue;
                 unsigned v = 0;
@@ -479,7 +481,7 @@ quad_kernel(const QuadArgs A)
                 A.packed[(size_t)(frame0 + f) * wpf + w] = v;
             }
         }
-        if (tid < kFramesPerCta && frame0 + tid < A.B) {
+        if (tid < FR && frame0 + tid < A.B) {
             frames_done += 1;
             frm_err += flags[tid];
         }
@@ -509,9 +511,10 @@ quad_kernel(const QuadArgs A)
 // ---------------------------------------------------------------------------
 static size_t quad_smem_bytes(const QuadGeom &g)
 {
+    const int areas = g.frames + (g.frames < kFramesPerCta);
     size_t tab = ((size_t)7 * g.N * 2 + 15) / 16 * 16;
-    size_t fl = (size_t)kFramesPerCta * g.rec_stride + (size_t)kFramesPerCta * g.ck_stride + 4 * kXchFloats;
-    return tab + fl * 4 + 16 * 4 + (size_t)kFramesPerCta * g.N;
+    size_t fl = (size_t)areas * g.rec_stride + (size_t)areas * g.ck_stride + 4 * kXchFloats;
+    return tab + fl * 4 + 16 * 4 + (size_t)g.frames * g.N;
 }
 
 int quad_configure(Codec &c)
@@ -529,14 +532,17 @@ int quad_configure(Codec &c)
     int ck = (g.nckA + g.nckB) * 16;
     if ((ck % 32) == 0) ck += 16;                   // == 16 (mod 32)
     g.ck_stride = ck;
-    g.frames = kFramesPerCta;
-    g.smem_bytes = quad_smem_bytes(g);
     int dev = 0;
     cudaDeviceProp prop;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
     c.num_sms = prop.multiProcessorCount;
-    if (g.smem_bytes > (size_t)prop.sharedMemPerBlockOptin) return B200DVB_ENOSPEC;
+    // as many frames per CTA (8, 4, 2, 1) as the branch-metric records leave room for
+    for (g.frames = kFramesPerCta; g.frames >= 1; g.frames >>= 1) {
+        g.smem_bytes = quad_smem_bytes(g);
+        if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) break;
+    }
+    if (g.frames < 1) return B200DVB_ENOSPEC;
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     int occ = 0;
@@ -548,18 +554,18 @@ int quad_configure(Codec &c)
 
 static int grid_for(const Codec &c, int B)
 {
-    const int groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    const int groups = (B + c.geom.frames - 1) / c.geom.frames;
     const int cap = c.num_sms * c.geom.ctas_per_sm;
     return groups < cap ? groups : cap;
 }
 
 size_t decode_workspace_bytes(const Codec &c, int B)
 {
-    return (size_t)3 * grid_for(c, B) * kFramesPerCta * c.N * sizeof(double2) + 256;
+    return (size_t)3 * grid_for(c, B) * c.geom.frames * c.N * sizeof(double2) + 256;
 }
 size_t siso_workspace_bytes(const Codec &c, int B)
 {
-    return (size_t)grid_for(c, B) * kFramesPerCta * c.N * sizeof(double2) + 256;
+    return (size_t)grid_for(c, B) * c.geom.frames * c.N * sizeof(double2) + 256;
 }
 
 static inline unsigned char *align256(void *p)
@@ -574,10 +580,10 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
     if (B == 0) return B200DVB_OK;
     if (ws_bytes < decode_workspace_bytes(c, B)) return B200DVB_ENOMEM;
     const int grid = grid_for(c, B);
-    const size_t per = (size_t)grid * kFramesPerCta * c.N;
+    const size_t per = (size_t)grid * c.geom.frames * c.N;
     QuadArgs A{};
     A.g = c.geom; A.B = B; A.iterations = c.iterations;
-    A.n_groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    A.n_groups = (B + c.geom.frames - 1) / c.geom.frames;
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;
@@ -597,7 +603,7 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
     const int grid = grid_for(c, B);
     QuadArgs A{};
     A.g = c.geom; A.B = B; A.iterations = 1;
-    A.n_groups = (B + kFramesPerCta - 1) / kFramesPerCta;
+    A.n_groups = (B + c.geom.frames - 1) / c.geom.frames;
     A.tab = c.d_tab;
     A.LcA = Lc_A; A.LcB = Lc_B; A.LcW = Lc_W; A.LcY = Lc_Y; A.LaA = La_A; A.LaB = La_B;
     A.LeA = Le_A; A.LeB = Le_B; A.siso_sf = sf;

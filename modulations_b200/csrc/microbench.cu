@@ -3,7 +3,7 @@
 // nominal 64 ACS/clk/SM of SURVEY §8(d) AND against these measured pipes.
 //
 // results[0] FADD   results[1] FMNMX   results[2] ACS mix (2 FADD + 1 FMNMX)
-// results[3] SHFL   results[4] DADD    results[5] F2F.F32.F64
+// results[3] SHFL   results[4] DADD    results[5] F2F (f64<->f32 conversions)
 // results[6] add.f32x2 (counted as 2 lane-ops)   results[7] SM clock in MHz
 #include "common.cuh"
 
@@ -37,7 +37,10 @@ __global__ void __launch_bounds__(1024) probe(float seed, long long *cycles, flo
             }
             if (OP == 3) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+f"(x[i]));
             if (OP == 4) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"((double)c));
-            if (OP == 5) asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(x[i]) : "d"(d[i]));
+            if (OP == 5) {
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(x[i]) : "d"(d[i]));
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[i]) : "f"(x[i]));
+            }
             if (OP == 6) {
                 unsigned long long p, q;
                 asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x[i]), "f"(x[(i + 1) % kChains]));
@@ -91,7 +94,7 @@ int run_microbench(double *r)
     if (rc == 0) rc = run_one<2>(sms, d_cycles, d_sink, 1, r + 2);   // one ACS per iteration
     if (rc == 0) rc = run_one<3>(sms, d_cycles, d_sink, 1, r + 3);
     if (rc == 0) rc = run_one<4>(sms, d_cycles, d_sink, 1, r + 4);
-    if (rc == 0) rc = run_one<5>(sms, d_cycles, d_sink, 1, r + 5);
+    if (rc == 0) rc = run_one<5>(sms, d_cycles, d_sink, 2, r + 5);   // two conversions per iteration
     if (rc == 0) rc = run_one<6>(sms, d_cycles, d_sink, 2, r + 6);
     r[7] = khz / 1000.0;
     cudaFree(d_cycles);

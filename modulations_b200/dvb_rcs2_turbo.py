@@ -356,7 +356,8 @@ class DVBRCS2_Turbo:
                                          and counters.element_size() == 8 and counters.numel() >= 4):
             raise ValueError("counters must be a CUDA int64/uint64 tensor with 4 elements")
         ws, need = h.workspace("decode", B)
-        rc = _lib.load().b200dvb_decode(h.h, B, _lib.ptr(x), x.stride(0), _lib.ptr(bits),
+        stride = x.stride(0) if B > 1 else x.shape[1]     # a length-1 axis may report stride 0
+        rc = _lib.load().b200dvb_decode(h.h, B, _lib.ptr(x), stride, _lib.ptr(bits),
                                         _lib.ptr(packed), _lib.ptr(ref), _lib.ptr(counters),
                                         _lib.ptr(ws), need, _lib.stream_ptr())
         _lib.check(rc, "decode")

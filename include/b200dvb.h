@@ -150,6 +150,12 @@ int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
                              uint8_t *info_out, uint8_t *coded_out, float *llr_out,
                              void *stream);
 
+/* Complex AWGN channel, in place: iq[i] += sigma*(n_re + j*n_im), Philox-keyed by
+ * (seed, offset + i) so a sharded run draws the same noise as a single-GPU run
+ * (channel model of test.py:66-68).  iq float2[n_sym]; offset must be even. */
+int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
+                         unsigned long long offset, void *iq, void *stream);
+
 /* Small device-throughput probes used by bench.py to state the ALU roofline
  * (FADD / FMNMX / SHFL lane-ops per clock per SM).  results_h: double[8]. */
 int b200dvb_microbench(double *results_h);

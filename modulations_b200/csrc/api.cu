@@ -247,6 +247,13 @@ int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
                           (cudaStream_t)stream);
 }
 
+int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
+                         unsigned long long offset, void *iq, void *stream)
+{
+    if (!iq || !(sigma >= 0.f)) return B200DVB_EINVAL;
+    return launch_awgn_complex(n_sym, sigma, seed, offset, iq, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------
 static const int kBps[6] = {1, 2, 3, 4, 6, 8};
 
@@ -287,7 +294,7 @@ int b200dvb_modem_create(int mod_id, const double *table_h, b200dvb_modem_t *out
         delete h;
         return B200DVB_ECUDA;
     }
-    if (m.separable) {
+    if (m.separable && !getenv("B200DVB_FORCE_GENERIC_DEMAP")) {
         int rc = modem_build_pwl(m);
         if (rc != B200DVB_OK) { cudaFree(m.d_table64); cudaFree(m.d_table32); delete h; return rc; }
     }

@@ -80,6 +80,9 @@ int launch_mc_bpsk(const Codec &c, int B, float noise_var, unsigned long long se
                    unsigned long long frame_offset, uint8_t *info, uint8_t *coded, float *llr,
                    cudaStream_t s);
 
+int launch_awgn_complex(size_t n, float sigma, unsigned long long seed, unsigned long long offset,
+                        void *iq, cudaStream_t s);
+
 int launch_map(const Modem &m, size_t n, const uint8_t *bits, void *iq, int out_f64, cudaStream_t s);
 int launch_demap(const Modem &m, size_t n, const void *iq, float noise_var, float scale,
                  float *llr, cudaStream_t s);

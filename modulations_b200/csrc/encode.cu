@@ -137,6 +137,28 @@ __global__ void awgn_bpsk_kernel(size_t n4, size_t n, float sigma, float two_ove
     }
 }
 
+// Complex AWGN added in place: iq[i] += sigma * (n_re + j n_im); 2 symbols per thread.
+__global__ void awgn_complex_kernel(size_t n2, size_t n, float sigma, unsigned long long seed,
+                                    unsigned long long offset2, float2 *__restrict__ iq)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const Philox r = philox(offset2 + i, 3u, seed);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const size_t e = 2 * i + h;
+        if (e >= n) break;
+        const float u1 = ((float)r.c[2 * h] + 0.5f) * 2.3283064365386963e-10f;
+        const float u2 = ((float)r.c[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
+        const float rad = sigma * sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        float2 v = iq[e];
+        v.x += rad * cs; v.y += rad * sn;
+        iq[e] = v;
+    }
+}
+
 int odd_words(int bytes)
 {
     int w = (bytes + 3) / 4;
@@ -186,6 +208,17 @@ int launch_mc_bpsk(const Codec &c, int B, float noise_var, unsigned long long se
     awgn_bpsk_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
         n4, n, sqrtf(noise_var), 2.0f / noise_var, seed,
         frame_offset * (unsigned long long)c.n_llr / 4ull, coded, llr);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+int launch_awgn_complex(size_t n, float sigma, unsigned long long seed, unsigned long long offset,
+                        void *iq, cudaStream_t s)
+{
+    if (n == 0) return B200DVB_OK;
+    const size_t n2 = (n + 1) / 2;
+    awgn_complex_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(n2, n, sigma, seed, offset / 2,
+                                                                    reinterpret_cast<float2 *>(iq));
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

@@ -366,6 +366,46 @@ class DVBRCS2_Turbo:
             res = res.cpu().numpy()
         return res
 
+    def decode_batch_host(self, llr_host, out_host=None, chunk=32768):
+        """End-to-end decode of HOST buffers: pinned ``llr_host`` float32 [B, n_llr] ->
+        pinned ``out_host`` int32 [B, 2N].  Chunks are pipelined over three CUDA streams
+        so the host->device copy of chunk i+1, the decode of chunk i and the
+        device->host copy of chunk i-1 overlap.  Returns out_host (a torch CPU tensor)."""
+        torch = _lib.require_cuda()
+        h = self.handle
+        x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(llr_host, np.float32))
+        if x.dim() != 2 or x.shape[1] < h.n_llr:
+            raise IndexError(f"llr needs shape [B, >= {h.n_llr}]")
+        B, width = x.shape
+        if out_host is None:
+            out_host = torch.empty((B, self.k_info), dtype=torch.int32, pin_memory=True)
+        nstage = 3
+        if getattr(self, "_e2e", None) is None or self._e2e[0] != (chunk, width):
+            streams = [torch.cuda.Stream(device=h.device) for _ in range(nstage)]
+            din = [torch.empty((chunk, width), dtype=torch.float32, device=h.device) for _ in range(nstage)]
+            dout = [torch.empty((chunk, self.k_info), dtype=torch.int32, device=h.device) for _ in range(nstage)]
+            need = int(_lib.load().b200dvb_decode_workspace_bytes(h.h, chunk))
+            wss = [torch.empty(need, dtype=torch.uint8, device=h.device) for _ in range(nstage)]
+            self._e2e = ((chunk, width), streams, din, dout, wss, need)
+        _, streams, din, dout, wss, need = self._e2e
+        lib = _lib.load()
+        cur = torch.cuda.current_stream(h.device)
+        for st in streams:
+            st.wait_stream(cur)
+        for i, lo in enumerate(range(0, B, chunk)):
+            n = min(chunk, B - lo)
+            j = i % nstage
+            with torch.cuda.stream(streams[j]):
+                din[j][:n].copy_(x[lo:lo + n], non_blocking=True)
+                rc = lib.b200dvb_decode(h.h, n, _lib.ptr(din[j]), width, _lib.ptr(dout[j]), None, None,
+                                        None, _lib.ptr(wss[j]), need,
+                                        ctypes.c_void_p(streams[j].cuda_stream))
+                _lib.check(rc, "decode")
+                out_host[lo:lo + n].copy_(dout[j][:n], non_blocking=True)
+        for st in streams:
+            cur.wait_stream(st)
+        return out_host
+
     def decode(self, llr):
         """Decode one frame of LLRs (positive = bit 0) into 2N info bits, int32 (:464-537)."""
         llr = np.array(llr, dtype=np.float32)

@@ -156,6 +156,11 @@ int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
 int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
                          unsigned long long offset, void *iq, void *stream);
 
+/* Diagnostics: SM cycles the decoder CTAs spent per phase since the last reset, summed
+ * over CTAs (synchronises the device).  out8_h: double[8] = {prep, recursion-in,
+ * recursion-out + extrinsic, epilogue, hard decision, CTA total, 0, 0}. */
+int b200dvb_debug_phase_cycles(double *out8_h, int reset);
+
 /* Small device-throughput probes used by bench.py to state the ALU roofline
  * (FADD / FMNMX / SHFL lane-ops per clock per SM).  results_h: double[8]. */
 int b200dvb_microbench(double *results_h);

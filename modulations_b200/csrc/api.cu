@@ -166,6 +166,14 @@ int b200dvb_codec_create(int N, const int32_t *next_state_h, const int32_t *out_
             c.h_tab[(3 + j) * N + i] = punct_h[j * period + p] ? (int16_t)idx++ : (int16_t)-1;
     }
     c.n_llr = idx;
+    c.vec_ab = 1; c.vec_wy = 1;
+    for (int i = 0; i < N; ++i) {
+        if (c.h_tab[2 * N + i] & 1) c.vec_ab = 0;
+        for (int e = 0; e < 2; ++e) {
+            const int ow = c.h_tab[(3 + 2 * e) * N + i], oy = c.h_tab[(4 + 2 * e) * N + i];
+            if (ow < 0 || oy != ow + 1 || (ow & 1)) c.vec_wy = 0;
+        }
+    }
     if (idx > 32767) { free(c.h_tab); delete h; return B200DVB_ENOSPEC; }
     cudaError_t e = cudaMalloc(&c.d_tab, sizeof(int16_t) * 7 * N);
     if (e == cudaSuccess)
@@ -331,6 +339,12 @@ int b200dvb_hard_demod(b200dvb_modem_t modem, size_t n_sym, const void *iq, int 
 {
     if (!modem || !iq || !bits) return B200DVB_EINVAL;
     return launch_hard(modem->m, n_sym, iq, in_f64, bits, (cudaStream_t)stream);
+}
+
+int b200dvb_debug_phase_cycles(double *out8_h, int reset)
+{
+    if (!out8_h) return B200DVB_EINVAL;
+    return read_phase_cycles(out8_h, reset);
 }
 
 int b200dvb_microbench(double *results_h)

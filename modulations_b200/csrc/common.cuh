@@ -22,17 +22,22 @@ constexpr int kMaxN = 2048;
 
 // ---- decoder geometry (decode_quad.cu) --------------------------------------
 constexpr int kFramesPerCta = 8;    // one 4-lane "quad" per frame and direction
-constexpr int kCtaThreads = 64;     // warp 0: forward (alpha), warp 1: backward (beta)
+constexpr int kCtaThreads = 64;     // per group: one forward (alpha) warp + one backward (beta) warp
+constexpr int kMaxGroups = 7;       // groups (of 8 frames) per CTA
+constexpr int kMaxCtaThreads = 448; // 14 warps: 2 per group + helper warps for the data-parallel phases
 constexpr int kWin = 8;             // checkpoint spacing / recompute window (steps)
 
 struct QuadGeom {
     int N;            // couples per frame
+    unsigned magic;   // floor(2^32 / N) + 1: flat position -> (frame, step) without a divide
     int M;            // crossing point: alpha warp owns [M,N), beta warp owns [0,M)
     int nckA;         // alpha checkpoints (alpha[0], alpha[8], ... alpha[M-8])
     int nckB;         // beta checkpoints, one per alpha-warp window end
     int rec_stride;   // floats between two frames' branch-metric records (8N + 8)
     int ck_stride;    // floats between two frames' checkpoint areas
-    int frames;       // frames per CTA actually used (<= kFramesPerCta)
+    int groups;       // (alpha warp, beta warp) pairs per CTA
+    int threads;      // CTA size: 64 * groups recursion threads + helper warps
+    int frames;       // frames per CTA (8 * groups, or 4/2/1 when even one group does not fit)
     int ctas_per_sm;
     size_t smem_bytes;
 };
@@ -42,6 +47,7 @@ struct Codec {
     double sf_inner = 0.7, sf_last = 1.0;
     QuadGeom geom{};
     int num_sms = 0;
+    int vec_ab = 0, vec_wy = 0;   // (A,B) / (W,Y) LLR pairs are adjacent and even-aligned in the stream
     // device tables
     int16_t *d_tab = nullptr;     // [7][N] int16: perm, inv_perm, offA, offW1, offY1, offW2, offY2
     // host tables
@@ -73,6 +79,7 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
 size_t decode_workspace_bytes(const Codec &c, int B);
 size_t siso_workspace_bytes(const Codec &c, int B);
 int quad_configure(Codec &c);
+int read_phase_cycles(double *out_h, int reset);
 
 int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,
                   cudaStream_t s);

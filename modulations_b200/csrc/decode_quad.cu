@@ -27,6 +27,8 @@
 //     perm / inv_perm tables (never assumed bijective).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b200dvb {
 
 namespace {
@@ -48,11 +50,24 @@ struct QuadArgs {
     const double *LaA, *LaB;
     double *LeA, *LeB;
     double siso_sf;
+    int vec_ab, vec_wy;   // 8-byte loads of (A,B) / (W,Y) pairs are legal for this codec + stride
     // workspace
     double2 *Le1, *Le2, *Y;
 };
 
-constexpr int kXchFloats = 144;   // one exchange buffer (8 quads, skewed), see xbase()
+// phase timers (SM cycles summed over CTAs): 0 prep, 1 recursion in (pass 1 + pass 2 to the
+// crossing point), 2 recursion out (windows + extrinsic), 3 epilogue, 4 hard decision, 5 CTA total
+__device__ unsigned long long g_phase_cycles[8];
+
+constexpr int kXchFloats = 144;
+constexpr int kBatch = 4;          // positions per thread whose loads are issued together (prep / epilogue)   // one exchange buffer (8 quads, skewed), see xbase()
+
+// flat position index -> (frame slot f, step k); magic = floor(2^32 / N) + 1 (exact for i*N < 2^32)
+__device__ __forceinline__ void split_pos(int i, int N, unsigned magic, int &f, int &k)
+{
+    f = (int)__umulhi((unsigned)i, magic);
+    k = i - f * N;
+}
 
 __device__ __forceinline__ int cls2(int s)
 {   // 2 * class(s): class = 2*(s0^s1^s2) + s1  (w = A^B^s0^s1^s2, y = A^B^s1)
@@ -61,7 +76,7 @@ __device__ __forceinline__ int cls2(int s)
 }
 
 struct Lane {
-    int q;         // quad (frame within CTA)
+    int q;         // quad (frame within CTA, or the scratch area for idle quads)
     int p;         // lane within quad
     int oA[2];     // float offset of butterfly A's (g0,g1) pair inside a record, by parity of k
     int oB[2];     // same for butterfly B
@@ -74,6 +89,39 @@ struct Lane {
 // quarter-warp and the column reads of a full warp are both bank-conflict free.
 __device__ __forceinline__ int xbase(int q) { return 16 * q + 4 * (q >> 1); }
 
+// Branch-metric pairs of one lane for two consecutive steps (even k, then k+1), and
+// the complementary-class pairs the extrinsic stage needs.
+struct G2 { float2 a0, b0, a1, b1; };
+struct GH { float2 gA, gB, hA, hB; };
+
+struct Recs {           // per-lane pointers into this frame's records
+    const float *pA0, *pB0, *pA1, *pB1;     // (g0,g1) of butterfly A/B in record k (even) / k+1
+    int dA0, dB0, dA1, dB1;                 // float distance from the g pair to the h pair (class ~c)
+    __device__ __forceinline__ G2 pair(int k_even) const {
+        G2 g;
+        g.a0 = *reinterpret_cast<const float2 *>(pA0 + k_even * 8);
+        g.b0 = *reinterpret_cast<const float2 *>(pB0 + k_even * 8);
+        g.a1 = *reinterpret_cast<const float2 *>(pA1 + k_even * 8);
+        g.b1 = *reinterpret_cast<const float2 *>(pB1 + k_even * 8);
+        return g;
+    }
+    template <int KPAR> __device__ __forceinline__ void one(int k, float2 &gA, float2 &gB) const {
+        const int e = (k - KPAR) * 8;
+        gA = *reinterpret_cast<const float2 *>((KPAR ? pA1 : pA0) + e);
+        gB = *reinterpret_cast<const float2 *>((KPAR ? pB1 : pB0) + e);
+    }
+    template <int KPAR> __device__ __forceinline__ GH ext(int k) const {
+        const int e = (k - KPAR) * 8;
+        const float *a = (KPAR ? pA1 : pA0) + e, *b = (KPAR ? pB1 : pB0) + e;
+        GH g;
+        g.gA = *reinterpret_cast<const float2 *>(a);
+        g.gB = *reinterpret_cast<const float2 *>(b);
+        g.hA = *reinterpret_cast<const float2 *>(a + (KPAR ? dA1 : dA0));
+        g.hB = *reinterpret_cast<const float2 *>(b + (KPAR ? dB1 : dB0));
+        return g;
+    }
+};
+
 __device__ __forceinline__ void norm4(float (&r)[4])
 {   // alpha[k+1,:] -= alpha[k+1,0]  (dvb_rcs2_turbo.py:178-179, :212-213)
     float n = __shfl_sync(0xffffffffu, r[0], 0, 4);
@@ -81,11 +129,10 @@ __device__ __forceinline__ void norm4(float (&r)[4])
     r[2] = __fsub_rn(r[2], n); r[3] = __fsub_rn(r[3], n);
 }
 
-template <int KPAR>
-__device__ __forceinline__ void step(float (&r)[4], const float *rec, const Lane &L)
+// One trellis step on the 4 states of a lane: butterfly A on (r0,r2) with (g0,g1) =
+// (gA.x,gA.y), butterfly B on (r1,r3) with (g0,g1) = (gB.y,gB.x); then normalise.
+__device__ __forceinline__ void stepg(float (&r)[4], const float2 gA, const float2 gB)
 {
-    const float2 gA = *reinterpret_cast<const float2 *>(rec + L.oA[KPAR]);
-    const float2 gB = *reinterpret_cast<const float2 *>(rec + L.oB[KPAR]);
     float o0 = fmaxf(__fadd_rn(r[0], gA.x), __fadd_rn(r[2], gA.y));
     float o1 = fmaxf(__fadd_rn(r[0], gA.y), __fadd_rn(r[2], gA.x));
     float o2 = fmaxf(__fadd_rn(r[1], gB.y), __fadd_rn(r[3], gB.x));
@@ -113,33 +160,16 @@ struct Xch {            // two alternating exchange buffers: one __syncwarp per 
     __device__ __forceinline__ float *next() { float *t = b0; b0 = b1; b1 = t; return t; }
 };
 
-// alpha[k] -> alpha[k+1] for k, k+1 (k even), ending in boundary layout
-__device__ __forceinline__ void fwd2(float (&r)[4], const float *rec, const Lane &L, Xch &x)
-{
-    step<0>(r, rec, L);
-    step<1>(r, rec + 8, L);
-    transpose_fwd(r, x.next(), L);
-}
-// beta[j] -> beta[j-2] (j even): uses gamma[j-1] (odd) then gamma[j-2] (even)
-__device__ __forceinline__ void bwd2(float (&r)[4], const float *rec_jm2, const Lane &L, Xch &x)
-{
-    step<1>(r, rec_jm2 + 8, L);
-    step<0>(r, rec_jm2, L);
-    transpose_bwd(r, x.next(), L);
-}
-
 // Extrinsic for step k (dvb_rcs2_turbo.py:239-248) fused with the owning
 // direction's recursion step.  a = alpha[k], b = beta[k+1] in matching layouts.
 // Writes (U0, U3, V1, V2) = max over states of the four branch-pair metrics into
-// words 0..3 of record k (gamma[k] is dead after this step).
+// words 0..3 of record k (gamma[k] is dead after this step; its values were
+// loaded into `G` before the call).
 template <int KPAR, bool OWN_ALPHA>
-__device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], float *rec, const Lane &L,
-                                         Xch &x)
+__device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], const GH G, float *rec,
+                                         const Lane &L, Xch &x)
 {
-    const float2 gA = *reinterpret_cast<const float2 *>(rec + L.oA[KPAR]);
-    const float2 gB = *reinterpret_cast<const float2 *>(rec + L.oB[KPAR]);
-    const float2 hA = *reinterpret_cast<const float2 *>(rec + 6 - L.oA[KPAR]);
-    const float2 hB = *reinterpret_cast<const float2 *>(rec + 6 - L.oB[KPAR]);
+    const float2 gA = G.gA, gB = G.gB, hA = G.hA, hB = G.hB;
     // butterfly A: x = (a0,a2) y = (b0,b2) g = (gA.x,gA.y) h = (hA.x,hA.y)
     const float a0g0 = __fadd_rn(a[0], gA.x), a2g0 = __fadd_rn(a[2], gA.x);
     const float a0g1 = __fadd_rn(a[0], gA.y), a2g1 = __fadd_rn(a[2], gA.y);
@@ -167,138 +197,179 @@ __device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], float *re
         a[0] = o0; a[1] = o1; a[2] = o2; a[3] = o3;
         norm4(a);
     } else {
-        float o0 = fmaxf(__fadd_rn(b[0], gA.x), __fadd_rn(b[2], gA.y));
-        float o1 = fmaxf(__fadd_rn(b[0], gA.y), __fadd_rn(b[2], gA.x));
-        float o2 = fmaxf(__fadd_rn(b[1], gB.y), __fadd_rn(b[3], gB.x));
-        float o3 = fmaxf(__fadd_rn(b[1], gB.x), __fadd_rn(b[3], gB.y));
-        b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3;
-        norm4(b);
+        stepg(b, gA, gB);
     }
-    // cross-lane max: lane p collects role p from the four lanes of its quad.
-    // Roles (U0,V1,U3,V2); on odd k lanes 2,3 (p1 = 1) hold them as (V1,U0,V2,U3).
-    float *xb = x.next();
-    *reinterpret_cast<float4 *>(xb + L.xw) = T;
-    __syncwarp();
-    const int c01 = L.xr, c23 = (KPAR == 1) ? (L.xr ^ 1) : L.xr;
-    float v = fmaxf(fmaxf(xb[c01], xb[c01 + 4]), fmaxf(xb[c23 + 8], xb[c23 + 12]));
+    // cross-lane max by reduce-scatter over the quad: lane p ends up with role p of
+    // (U0,V1,U3,V2).  On odd k lanes 2,3 (p1 = 1) hold their partials as (V1,U0,V2,U3),
+    // so what they send and keep is swapped pairwise.  Pure register traffic: no
+    // barrier, and independent steps of a window overlap their shuffles.
+    const bool p1 = (L.p & 2) != 0, p0 = (L.p & 1) != 0;
+    float s0, s1, k0, k1;
+    if (KPAR == 0) {
+        s0 = p1 ? T.x : T.z; s1 = p1 ? T.y : T.w;
+        k0 = p1 ? T.z : T.x; k1 = p1 ? T.w : T.y;
+    } else {
+        s0 = p1 ? T.y : T.z; s1 = p1 ? T.x : T.w;
+        k0 = p1 ? T.w : T.x; k1 = p1 ? T.z : T.y;
+    }
+    k0 = fmaxf(k0, __shfl_xor_sync(0xffffffffu, s0, 2));
+    k1 = fmaxf(k1, __shfl_xor_sync(0xffffffffu, s1, 2));
+    const float snd = p0 ? k0 : k1, kp = p0 ? k1 : k0;
+    const float v = fmaxf(kp, __shfl_xor_sync(0xffffffffu, snd, 1));
     rec[L.role_word] = v;
 }
 
 // ---------------------------------------------------------------------------
-// One SISO over the 8 frames of this CTA.  Records must be complete and a
+// One SISO over the frames of this CTA.  Records must be complete and a
 // __syncthreads() must have been executed before the call; on return (after the
 // trailing __syncthreads) words 0..3 of every record hold (U0,U3,V1,V2).
+// Branch metrics are always loaded one step (or one step pair) ahead of their use:
+// the exchange-buffer stores in between would otherwise pin the loads behind them.
 // ---------------------------------------------------------------------------
 template <int LEN>
-__device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const float *ck, int j0,
-                                             const Lane &L, Xch &x)
+__device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const Recs &R,
+                                             const float *ck, int j0, const Lane &L, Xch &x)
 {
     float wb[LEN][4];
     {
         const float4 c = *reinterpret_cast<const float4 *>(ck);
         wb[LEN - 1][0] = c.x; wb[LEN - 1][1] = c.y; wb[LEN - 1][2] = c.z; wb[LEN - 1][3] = c.w;
     }
+    float2 gA, gB, nA, nB;
+    R.template one<(LEN - 1) & 1>(j0 + LEN - 1, gA, gB);
 #pragma unroll
     for (int i = LEN - 2; i >= 0; --i) {   // beta[j0+2+i] -> beta[j0+1+i] uses gamma[j0+1+i]
 #pragma unroll
         for (int t = 0; t < 4; ++t) wb[i][t] = wb[i + 1][t];
-        const float *rec = grec + (j0 + 1 + i) * 8;
-        if ((i + 1) & 1) {
-            step<1>(wb[i], rec, L);
-        } else {
-            step<0>(wb[i], rec, L);
-            transpose_bwd(wb[i], x.next(), L);
+        if (i > 0) {
+            if (i & 1) R.template one<1>(j0 + i, nA, nB); else R.template one<0>(j0 + i, nA, nB);
         }
+        stepg(wb[i], gA, gB);
+        if (((i + 1) & 1) == 0) transpose_bwd(wb[i], x.next(), L);
+        gA = nA; gB = nB;
     }
+    GH G = R.template ext<0>(j0), Gn = G;
 #pragma unroll
     for (int i = 0; i < LEN; ++i) {
         float *rec = grec + (j0 + i) * 8;
+        if (i + 1 < LEN) {
+            if ((i + 1) & 1) Gn = R.template ext<1>(j0 + i + 1); else Gn = R.template ext<0>(j0 + i + 1);
+        }
         if (i & 1) {
-            ext_step<1, true>(r, wb[i], rec, L, x);
+            ext_step<1, true>(r, wb[i], G, rec, L, x);
             transpose_fwd(r, x.next(), L);
         } else {
-            ext_step<0, true>(r, wb[i], rec, L, x);
+            ext_step<0, true>(r, wb[i], G, rec, L, x);
         }
+        G = Gn;
     }
 }
 
-__device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const float *ck, int j0,
-                                            const Lane &L, Xch &x)
+__device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Recs &R,
+                                            const float *ck, int j0, const Lane &L, Xch &x)
 {
     float wa[kWin][4];
     {
         const float4 c = *reinterpret_cast<const float4 *>(ck);
         wa[0][0] = c.x; wa[0][1] = c.y; wa[0][2] = c.z; wa[0][3] = c.w;
     }
+    float2 gA, gB, nA, nB;
+    R.template one<0>(j0, gA, gB);
 #pragma unroll
     for (int i = 1; i < kWin; ++i) {       // alpha[j0+i-1] -> alpha[j0+i] uses gamma[j0+i-1]
 #pragma unroll
         for (int t = 0; t < 4; ++t) wa[i][t] = wa[i - 1][t];
-        const float *rec = grec + (j0 + i - 1) * 8;
-        if ((i - 1) & 1) {
-            step<1>(wa[i], rec, L);
-            transpose_fwd(wa[i], x.next(), L);
-        } else {
-            step<0>(wa[i], rec, L);
+        if (i + 1 < kWin) {
+            if (i & 1) R.template one<1>(j0 + i, nA, nB); else R.template one<0>(j0 + i, nA, nB);
         }
+        stepg(wa[i], gA, gB);
+        if ((i - 1) & 1) transpose_fwd(wa[i], x.next(), L);
+        gA = nA; gB = nB;
     }
+    GH G = R.template ext<1>(j0 + kWin - 1), Gn = G;
 #pragma unroll
     for (int i = kWin - 1; i >= 0; --i) {
         float *rec = grec + (j0 + i) * 8;
+        if (i > 0) {
+            if ((i - 1) & 1) Gn = R.template ext<1>(j0 + i - 1); else Gn = R.template ext<0>(j0 + i - 1);
+        }
         if (i & 1) {
-            ext_step<1, false>(wa[i], r, rec, L, x);
+            ext_step<1, false>(wa[i], r, G, rec, L, x);
         } else {
-            ext_step<0, false>(wa[i], r, rec, L, x);
+            ext_step<0, false>(wa[i], r, G, rec, L, x);
             transpose_bwd(r, x.next(), L);
         }
+        G = Gn;
     }
 }
 
 __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *ckbuf, float *xch,
-                                          int warp, const Lane &L)
+                                          int warp, int wid, const Lane &L, long long &t_mid)
 {
     const int N = g.N, M = g.M;
     float *grec = gam + L.q * g.rec_stride;
     float *ckq = ckbuf + L.q * g.ck_stride + 4 * L.p;     // this lane's float4 slot, checkpoint 0
-    Xch x{xch + warp * 2 * kXchFloats, xch + warp * 2 * kXchFloats + kXchFloats};
+    Xch x{xch + wid * 2 * kXchFloats, xch + wid * 2 * kXchFloats + kXchFloats};
+    Recs R;
+    R.pA0 = grec + L.oA[0];     R.pB0 = grec + L.oB[0];
+    R.pA1 = grec + 8 + L.oA[1]; R.pB1 = grec + 8 + L.oB[1];
+    R.dA0 = 6 - 2 * L.oA[0]; R.dB0 = 6 - 2 * L.oB[0];
+    R.dA1 = 6 - 2 * L.oA[1]; R.dB1 = 6 - 2 * L.oB[1];
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (warp == 0) {
-        // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183)
-        for (int k = 0; k < N; k += 2) fwd2(r, grec + k * 8, L, x);
-        // pass 2, first half: checkpoints alpha[0], alpha[8], ...
-        for (int k = 0; k < M; k += 2) {
-            if ((k & (kWin - 1)) == 0)
+        // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183);
+        // pass 2 up to the crossing point M with a checkpoint every kWin steps.
+        G2 cur = R.pair(0);
+        for (int t = 0; t < N + M; t += 2) {
+            const int k = t < N ? t : t - N;
+            int kn = k + 2;
+            if (kn >= N) kn = 0;
+            const G2 nxt = R.pair(kn);
+            if (t >= N && (k & (kWin - 1)) == 0)
                 *reinterpret_cast<float4 *>(ckq + (k / kWin) * 16) = make_float4(r[0], r[1], r[2], r[3]);
-            fwd2(r, grec + k * 8, L, x);
+            stepg(r, cur.a0, cur.b0);
+            stepg(r, cur.a1, cur.b1);
+            transpose_fwd(r, x.next(), L);
+            cur = nxt;
         }
     } else {
-        for (int j = N; j > 0; j -= 2) bwd2(r, grec + (j - 2) * 8, L, x);   // :203-213, :216-217
-        for (int j = N; j > M; j -= 2) {
-            if (j == N || ((j - M) & (kWin - 1)) == 0) {
+        // beta: j = N..2 twice (:203-230), the second time only down to M
+        G2 cur = R.pair(N - 2);
+        for (int t = 0; t < 2 * N - M; t += 2) {
+            const int j = t < N ? N - t : 2 * N - t;
+            int jn = j - 2;
+            if (jn < 2) jn = N;
+            const G2 nxt = R.pair(jn - 2);
+            if (t >= N && (j == N || ((j - M) & (kWin - 1)) == 0)) {
                 const int w = (j - M + kWin - 1) / kWin - 1;
                 *reinterpret_cast<float4 *>(ckq + (g.nckA + w) * 16) = make_float4(r[0], r[1], r[2], r[3]);
             }
-            bwd2(r, grec + (j - 2) * 8, L, x);
+            stepg(r, cur.a1, cur.b1);      // gamma[j-1] (odd)
+            stepg(r, cur.a0, cur.b0);      // gamma[j-2] (even)
+            transpose_bwd(r, x.next(), L);
+            cur = nxt;
         }
     }
     __syncthreads();
+    t_mid = clock64();
     if (warp == 0) {
         for (int w = 0; w < g.nckB; ++w) {
             const int j0 = M + w * kWin;
             const float *ck = ckq + (g.nckA + w) * 16;
-            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, ck, j0, L, x);
-            else                window_alpha<4>(r, grec, ck, j0, L, x);
+            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, R, ck, j0, L, x);
+            else                window_alpha<4>(r, grec, R, ck, j0, L, x);
         }
     } else {
         for (int w = g.nckA - 1; w >= 0; --w)
-            window_beta(r, grec, ckq + w * 16, w * kWin, L, x);
+            window_beta(r, grec, R, ckq + w * 16, w * kWin, L, x);
     }
     __syncthreads();
 }
 
 // Branch-metric record for one trellis step (dvb_rcs2_turbo.py:131-160): float64
 // left-to-right sums rounded once to float32, then merged per (W,Y) class.
-__device__ __forceinline__ void make_record(float *rec, int k, double YA, double YB, float pW, float pY)
+__device__ __forceinline__ void make_record(int k, double YA, double YB, float pW, float pY,
+                                            float4 &lo4, float4 &hi4)
 {
     const double a = YA * 0.5, b = YB * 0.5;
     const double w = (double)pW * 0.5, y = (double)pY * 0.5;
@@ -319,8 +390,8 @@ __device__ __forceinline__ void make_record(float *rec, int k, double YA, double
         o[2 * c] = swap ? GM : GP;
         o[2 * c + 1] = swap ? GP : GM;
     }
-    *reinterpret_cast<float4 *>(rec) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4 *>(rec + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    lo4 = make_float4(o[0], o[1], o[2], o[3]);
+    hi4 = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 // Extrinsic epilogue for one step (dvb_rcs2_turbo.py:250-279).
@@ -340,29 +411,36 @@ __device__ __forceinline__ double2 make_extrinsic(const float4 uv, double YA, do
 }
 
 template <bool SISO_ONLY>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kMaxCtaThreads)
 quad_kernel(const QuadArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QuadGeom g = A.g;
     const int N = g.N;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int NT = blockDim.x;                       // recursion warps + helper warps (prep / epilogue only)
+    const int wid = tid >> 5;
+    const bool helper = wid >= 2 * g.groups;         // helper warps only take part in the data-parallel phases
+    const int warp = wid >= g.groups;                // 0: forward (alpha) warps, 1: backward (beta) warps
+    const int wgrp = helper ? 0 : (warp ? wid - g.groups : wid);   // 8-frame group this warp serves
     // ---- shared memory carve-up -------------------------------------------------
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((7 * N * 2 + 15) / 16) * 16;
     float *gam = reinterpret_cast<float *>(smem_raw + tab_bytes);
     const int FR = g.frames;                         // frames this CTA decodes at a time
-    const int areas = FR + (FR < kFramesPerCta);     // idle quads (q >= FR) share one scratch area
+    const int areas = FR + ((FR & 7) != 0);          // idle quads (frame slot >= FR) share one scratch area
     float *ckbuf = gam + areas * g.rec_stride;
     float *xch = ckbuf + areas * g.ck_stride;
-    int *flags = reinterpret_cast<int *>(xch + 4 * kXchFloats);
-    unsigned char *hb = reinterpret_cast<unsigned char *>(flags + 16);   // [8][N] hard-bit pairs
+    int *flags = reinterpret_cast<int *>(xch + 4 * g.groups * kXchFloats);
+    unsigned char *hb = reinterpret_cast<unsigned char *>(flags + 64);   // [8][N] hard-bit pairs
 
-    for (int i = tid; i < 7 * N; i += kCtaThreads) tab[i] = A.tab[i];
+    for (int i = tid; i < 7 * N; i += NT) tab[i] = A.tab[i];
+    const int P = FR * N;                   // (frame, step) positions of this CTA, dealt out flat
+    const unsigned magic = g.magic;
     const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
 
     Lane L;
-    L.q = min(lane >> 2, FR); L.p = lane & 3;
+    L.q = min(wgrp * 8 + (lane >> 2), FR); L.p = lane & 3;
     L.oA[0] = cls2(L.p);     L.oB[0] = cls2(L.p + 4);
     L.oA[1] = cls2(2 * L.p); L.oB[1] = cls2(2 * L.p + 1);
     L.xw = xbase(lane >> 2) + 4 * L.p;
@@ -370,6 +448,8 @@ quad_kernel(const QuadArgs A)
     L.role_word = ((L.p & 1) << 1) | (L.p >> 1);      // roles (U0,V1,U3,V2) -> words (0,2,1,3)
 
     unsigned long long bit_err = 0, frm_err = 0, frames_done = 0;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_start = clock64();
     const size_t slot0 = (size_t)blockIdx.x * FR * N;
     double2 *Le1 = A.Le1 + slot0, *Le2 = A.Le2 + slot0, *Yb = A.Y + slot0;
 
@@ -385,92 +465,154 @@ quad_kernel(const QuadArgs A)
             double2 *LeOut = second ? Le2 : Le1;
             const int16_t *t_oW = tab + (3 + 2 * second) * N, *t_oY = tab + (4 + 2 * second) * N;
             __syncthreads();   // tables loaded / previous phase finished with gam, Le
+            const long long t0 = clock64();
             // ---- prep: gather, a-priori add, branch-metric records ------------------
-            for (int f = 0; f < FR; ++f) {
-                const long long frame = frame0 + f;
-                const bool valid = frame < A.B;
-                float *grec = gam + f * g.rec_stride;
-                for (int k = tid; k < N; k += kCtaThreads) {
-                    float sA = 0.f, sB = 0.f, pW = 0.f, pY = 0.f;
-                    double2 La = make_double2(0.0, 0.0);
-                    if (valid) {
+            // kBatch positions per thread are loaded before any is consumed, so the
+            // dependent smem-index -> L2 gather round trips overlap.
+            for (int i0 = tid; i0 < P; i0 += kBatch * NT) {
+                float sA[kBatch], sB[kBatch], pW[kBatch], pY[kBatch];
+                double2 La[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                    const long long frame = frame0 + f;
+                    sA[u] = sB[u] = pW[u] = pY[u] = 0.f;
+                    La[u] = make_double2(0.0, 0.0);
+                    if (i < P && frame < A.B) {
                         if (SISO_ONLY) {
-                            const size_t i = (size_t)frame * N + k;
-                            sA = __ldg(A.LcA + i); sB = __ldg(A.LcB + i);
-                            pW = __ldg(A.LcW + i); pY = __ldg(A.LcY + i);
-                            if (A.LaA) La.x = __ldg(A.LaA + i);
-                            if (A.LaB) La.y = __ldg(A.LaB + i);
+                            const size_t e = (size_t)frame * N + k;
+                            sA[u] = __ldg(A.LcA + e); sB[u] = __ldg(A.LcB + e);
+                            pW[u] = __ldg(A.LcW + e); pY[u] = __ldg(A.LcY + e);
+                            if (A.LaA) La[u].x = __ldg(A.LaA + e);
+                            if (A.LaB) La[u].y = __ldg(A.LaB + e);
                         } else {
                             const float *Lf = A.llr + frame * A.llr_stride;
                             const int src = second ? t_perm[k] : k;
                             const int oa = t_offA[src];
-                            sA = __ldg(Lf + oa); sB = __ldg(Lf + oa + 1);
+                            if (A.vec_ab) {
+                                const float2 v = __ldg(reinterpret_cast<const float2 *>(Lf + oa));
+                                sA[u] = v.x; sB[u] = v.y;
+                            } else {
+                                sA[u] = __ldg(Lf + oa); sB[u] = __ldg(Lf + oa + 1);
+                            }
                             const int ow = t_oW[k], oy = t_oY[k];
-                            if (ow >= 0) pW = __ldg(Lf + ow);
-                            if (oy >= 0) pY = __ldg(Lf + oy);
-                            if (!first) La = __ldcg(LePrev + (size_t)f * N + (second ? src : (int)t_inv[k]));
+                            if (A.vec_wy) {          // both parities present, adjacent and 8-byte aligned
+                                const float2 v = __ldg(reinterpret_cast<const float2 *>(Lf + ow));
+                                pW[u] = v.x; pY[u] = v.y;
+                            } else {
+                                if (ow >= 0) pW[u] = __ldg(Lf + ow);
+                                if (oy >= 0) pY[u] = __ldg(Lf + oy);
+                            }
+                            if (!first) La[u] = __ldcg(LePrev + (size_t)f * N + (second ? src : (int)t_inv[k]));
                         }
                     }
-                    const double YA = __dadd_rn((double)sA, La.x);   // Lc_A[k] + La_A[k] (:135)
-                    const double YB = __dadd_rn((double)sB, La.y);
-                    make_record(grec + k * 8, k, YA, YB, pW, pY);
-                    __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                    // computed unconditionally (one basic block, so the independent
+                    // float64 chains of the batch interleave); only the stores are guarded
+                    const double YA = __dadd_rn((double)sA[u], La[u].x);   // Lc_A[k] + La_A[k] (:135)
+                    const double YB = __dadd_rn((double)sB[u], La[u].y);
+                    float4 lo4, hi4;
+                    make_record(k, YA, YB, pW[u], pY[u], lo4, hi4);
+                    if (i < P) {
+                        float *rec = gam + f * g.rec_stride + k * 8;
+                        *reinterpret_cast<float4 *>(rec) = lo4;
+                        *reinterpret_cast<float4 *>(rec + 4) = hi4;
+                        __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
+                    }
                 }
             }
             __syncthreads();
-            siso_core(g, gam, ckbuf, xch, warp, L);
+            const long long t1 = clock64();
+            long long t2;
+            if (!helper) {
+                siso_core(g, gam, ckbuf, xch, warp, wid, L, t2);
+            } else {
+                __syncthreads();
+                t2 = clock64();
+                __syncthreads();
+            }
+            const long long t3 = clock64();
             // ---- epilogue: extrinsic LLRs (float64) ---------------------------------
-            for (int f = 0; f < FR; ++f) {
-                const long long frame = frame0 + f;
-                if (frame >= A.B) break;
-                const float *grec = gam + f * g.rec_stride;
-                for (int k = tid; k < N; k += kCtaThreads) {
-                    const float4 uv = *reinterpret_cast<const float4 *>(grec + k * 8);
-                    const double2 Y = __ldcg(Yb + (size_t)f * N + k);
-                    const double2 e = make_extrinsic(uv, Y.x, Y.y, sf);
-                    if (SISO_ONLY) {
-                        A.LeA[(size_t)frame * N + k] = e.x;
-                        A.LeB[(size_t)frame * N + k] = e.y;
-                    } else {
-                        __stcg(LeOut + (size_t)f * N + k, e);
+            for (int i0 = tid; i0 < P; i0 += kBatch * NT) {
+                double2 Y[kBatch];
+                float4 uv[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                    Y[u] = make_double2(0.0, 0.0); uv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < P && frame0 + f < A.B) {
+                        Y[u] = __ldcg(Yb + (size_t)f * N + k);
+                        uv[u] = *reinterpret_cast<const float4 *>(gam + f * g.rec_stride + k * 8);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                    const long long frame = frame0 + f;
+                    const double2 e = make_extrinsic(uv[u], Y[u].x, Y[u].y, sf);
+                    if (i < P && frame < A.B) {
+                        if (SISO_ONLY) {
+                            A.LeA[(size_t)frame * N + k] = e.x;
+                            A.LeB[(size_t)frame * N + k] = e.y;
+                        } else {
+                            __stcg(LeOut + (size_t)f * N + k, e);
+                        }
                     }
                 }
             }
+            ph[0] += t1 - t0; ph[1] += t2 - t1; ph[2] += t3 - t2; ph[3] += clock64() - t3;
         }
         if (SISO_ONLY) continue;
         __syncthreads();
+        const long long t5 = clock64();
         // ---- hard decision (dvb_rcs2_turbo.py:526-537) + optional error counting ----
         if (tid < FR) flags[tid] = 0;
         __syncthreads();
-        for (int f = 0; f < FR; ++f) {
-            const long long frame = frame0 + f;
-            if (frame >= A.B) break;
-            const float *Lf = A.llr + frame * A.llr_stride;
-            int errs = 0;
-            for (int j = tid; j < N; j += kCtaThreads) {
-                const int oa = t_offA[j];
-                const double2 La = __ldcg(Le2 + (size_t)f * N + t_inv[j]);
-                const double2 e1 = __ldcg(Le1 + (size_t)f * N + j);
-                const double LA = __dadd_rn(__dadd_rn((double)__ldg(Lf + oa), La.x), e1.x);
-                const double LB = __dadd_rn(__dadd_rn((double)__ldg(Lf + oa + 1), La.y), e1.y);
-                const int bA = LA < 0.0, bB = LB < 0.0;
-                if (A.bits)
-                    *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * j) = make_int2(bA, bB);
-                hb[f * N + j] = (unsigned char)(bA | (bB << 1));
-                if (A.ref_bits) {
-                    const uchar2 rb = *reinterpret_cast<const uchar2 *>(A.ref_bits + (size_t)frame * 2 * N + 2 * j);
-                    errs += (bA != rb.x) + (bB != rb.y);
+        for (int i0 = tid; i0 < P; i0 += kBatch * NT) {
+            double2 La[kBatch], e1[kBatch];
+            float sA[kBatch], sB[kBatch];
+            uchar2 rb[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                int f, j; const int i = i0 + u * NT; split_pos(i, N, magic, f, j);
+                const long long frame = frame0 + f;
+                La[u] = e1[u] = make_double2(0.0, 0.0); sA[u] = sB[u] = 0.f; rb[u] = make_uchar2(0, 0);
+                if (i < P && frame < A.B) {
+                    const float *Lf = A.llr + frame * A.llr_stride;
+                    const int oa = t_offA[j];
+                    La[u] = __ldcg(Le2 + (size_t)f * N + t_inv[j]);
+                    e1[u] = __ldcg(Le1 + (size_t)f * N + j);
+                    sA[u] = __ldg(Lf + oa); sB[u] = __ldg(Lf + oa + 1);
+                    if (A.ref_bits)
+                        rb[u] = *reinterpret_cast<const uchar2 *>(A.ref_bits + (size_t)frame * 2 * N + 2 * j);
                 }
             }
-            if (A.ref_bits) {
-                bit_err += errs;
-                if (errs) atomicOr(&flags[f], 1);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                int f, j; const int i = i0 + u * NT; split_pos(i, N, magic, f, j);
+                const long long frame = frame0 + f;
+                if (i < P && frame < A.B) {
+                    const double LA = __dadd_rn(__dadd_rn((double)sA[u], La[u].x), e1[u].x);
+                    const double LB = __dadd_rn(__dadd_rn((double)sB[u], La[u].y), e1[u].y);
+                    const int bA = LA < 0.0, bB = LB < 0.0;
+                    if (A.bits)
+                        *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * j) = make_int2(bA, bB);
+                    hb[f * N + j] = (unsigned char)(bA | (bB << 1));
+                    if (A.ref_bits) {
+                        const int errs = (bA != rb[u].x) + (bB != rb[u].y);
+                        bit_err += errs;
+                        if (errs) atomicOr(&flags[f], 1);
+                    }
+                }
             }
         }
         __syncthreads();
         if (A.packed) {
             const int wpf = (2 * N + 31) / 32;
-            for (int i = tid; i < FR * wpf; i += kCtaThreads) {
+            for (int i = tid; i < FR * wpf; i += NT) {
                 const int f = i / wpf, w = i - f * wpf;
                 if (frame0 + f >= A.B) continue;
                 unsigned v = 0;
@@ -481,10 +623,15 @@ quad_kernel(const QuadArgs A)
                 A.packed[(size_t)(frame0 + f) * wpf + w] = v;
             }
         }
+        ph[4] += clock64() - t5;
         if (tid < FR && frame0 + tid < A.B) {
             frames_done += 1;
             frm_err += flags[tid];
         }
+    }
+    if (tid == 0) {
+        ph[5] = clock64() - t_start;
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)ph[i]);
     }
     if (!SISO_ONLY && A.counters) {
         // one atomic per warp and counter at kernel end
@@ -511,10 +658,10 @@ quad_kernel(const QuadArgs A)
 // ---------------------------------------------------------------------------
 static size_t quad_smem_bytes(const QuadGeom &g)
 {
-    const int areas = g.frames + (g.frames < kFramesPerCta);
+    const int areas = g.frames + ((g.frames & 7) != 0);
     size_t tab = ((size_t)7 * g.N * 2 + 15) / 16 * 16;
-    size_t fl = (size_t)areas * g.rec_stride + (size_t)areas * g.ck_stride + 4 * kXchFloats;
-    return tab + fl * 4 + 16 * 4 + (size_t)g.frames * g.N;
+    size_t fl = (size_t)areas * g.rec_stride + (size_t)areas * g.ck_stride + 4 * g.groups * kXchFloats;
+    return tab + fl * 4 + 64 * 4 + (size_t)g.frames * g.N;
 }
 
 int quad_configure(Codec &c)
@@ -528,6 +675,7 @@ int quad_configure(Codec &c)
     if (g.M <= 0 || g.M >= N) return B200DVB_ENOSPEC;
     g.nckA = g.M / kWin;
     g.nckB = (N - g.M + kWin - 1) / kWin;
+    g.magic = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     g.rec_stride = 8 * N + 8;                       // == 8 (mod 32): 4 frames tile the 32 banks
     int ck = (g.nckA + g.nckB) * 16;
     if ((ck % 32) == 0) ck += 16;                   // == 16 (mod 32)
@@ -537,16 +685,36 @@ int quad_configure(Codec &c)
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
     c.num_sms = prop.multiProcessorCount;
-    // as many frames per CTA (8, 4, 2, 1) as the branch-metric records leave room for
-    for (g.frames = kFramesPerCta; g.frames >= 1; g.frames >>= 1) {
+    // One CTA per SM when possible: `groups` pairs of (alpha warp, beta warp), 8 frames per
+    // pair, all warps in the same phase so they share the instruction cache.  Fall back to
+    // fewer groups, then to fewer frames in a single group (8, 4, 2, 1), as N grows.
+    const int want_groups = getenv("B200DVB_GROUPS") ? atoi(getenv("B200DVB_GROUPS")) : kMaxGroups;
+    bool ok = false;
+    for (g.groups = want_groups < 1 ? 1 : (want_groups > kMaxGroups ? kMaxGroups : want_groups); g.groups >= 1 && !ok; --g.groups) {
+        g.frames = 8 * g.groups;
         g.smem_bytes = quad_smem_bytes(g);
-        if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) break;
+        if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) { ok = true; break; }
     }
-    if (g.frames < 1) return B200DVB_ENOSPEC;
+    if (!ok) {
+        g.groups = 1;
+        for (g.frames = 4; g.frames >= 1; g.frames >>= 1) {
+            g.smem_bytes = quad_smem_bytes(g);
+            if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) { ok = true; break; }
+        }
+    }
+    if (!ok) return B200DVB_ENOSPEC;
+    {
+        const char *e = getenv("B200DVB_THREADS");
+        int t = e ? atoi(e) : kMaxCtaThreads;
+        t = (t / 32) * 32;
+        if (t < kCtaThreads * g.groups) t = kCtaThreads * g.groups;
+        if (t > kMaxCtaThreads) t = kMaxCtaThreads;
+        g.threads = t;
+    }
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     int occ = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false>, kCtaThreads, g.smem_bytes));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false>, g.threads, g.smem_bytes));
     if (occ < 1) return B200DVB_ENOSPEC;
     g.ctas_per_sm = occ;
     return B200DVB_OK;
@@ -587,9 +755,12 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;
+    const bool even = (llr_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 7) == 0);
+    A.vec_ab = even && c.vec_ab;
+    A.vec_wy = even && c.vec_wy;
     A.Le1 = reinterpret_cast<double2 *>(align256(ws));
     A.Le2 = A.Le1 + per; A.Y = A.Le2 + per;
-    quad_kernel<false><<<grid, kCtaThreads, c.geom.smem_bytes, s>>>(A);
+    quad_kernel<false><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }
@@ -609,8 +780,20 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
     A.LeA = Le_A; A.LeB = Le_B; A.siso_sf = sf;
     A.Y = reinterpret_cast<double2 *>(align256(ws));
     A.Le1 = A.Y; A.Le2 = A.Y;
-    quad_kernel<true><<<grid, kCtaThreads, c.geom.smem_bytes, s>>>(A);
+    quad_kernel<true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+int read_phase_cycles(double *out_h, int reset)
+{
+    unsigned long long h[8];
+    B2_CUDA(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof h));
+    for (int i = 0; i < 8; ++i) out_h[i] = (double)h[i];
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        B2_CUDA(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z));
+    }
     return B200DVB_OK;
 }
 

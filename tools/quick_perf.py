@@ -34,6 +34,11 @@ for (N, rate, B) in ((212, '1/3', int(sys.argv[1]) if len(sys.argv) > 1 else 262
     print(f"N={N} B={B}: {best:.2f} ms (avg {avg:.2f})  {fps/1e6:.3f} Mframes/s  {fps*2*N/1e9:.3f} Gbit/s info  "
           f"{fps*acs/1e12:.2f} TACS/s = {fps*acs/(64*148*1.965e9)*100:.1f}% of nominal ALU roofline; "
           f"BER={cnt[0]/cnt[3]:.4f} FER={cnt[1]/cnt[2]:.4f}")
+    ph = np.zeros(8); lib.b200dvb_debug_phase_cycles(_lib.host_ptr(ph), 1)
+    c.decode_batch(llr, ref_bits=info, counters=counters, out="none"); torch.cuda.synchronize()
+    lib.b200dvb_debug_phase_cycles(_lib.host_ptr(ph), 1)
+    tot = ph[5]
+    print("   phases: " + "  ".join(f"{n}={v/tot*100:.1f}%" for n, v in zip(["prep","rec_in","rec_out","epi","hard"], ph[:5])) + f"  (CTA-cycles total {tot:.3g})")
     t_gen, _ = timeit(lambda: lib.b200dvb_mc_generate_bpsk(h.h, B, nv, 1234, 0, _lib.ptr(info), _lib.ptr(coded), _lib.ptr(llr), _lib.stream_ptr()))
     print(f"   mc_generate: {t_gen:.2f} ms ({B/t_gen/1e3:.2f} Mframes/s)")
     del info, coded, llr

@@ -317,37 +317,62 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *
     R.dA1 = 6 - 2 * L.oA[1]; R.dB1 = 6 - 2 * L.oB[1];
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (warp == 0) {
-        // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183);
-        // pass 2 up to the crossing point M with a checkpoint every kWin steps.
+        // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183)
         G2 cur = R.pair(0);
-        for (int t = 0; t < N + M; t += 2) {
-            const int k = t < N ? t : t - N;
-            int kn = k + 2;
-            if (kn >= N) kn = 0;
-            const G2 nxt = R.pair(kn);
-            if (t >= N && (k & (kWin - 1)) == 0)
-                *reinterpret_cast<float4 *>(ckq + (k / kWin) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll 2
+        for (int k = 0; k < N; k += 2) {
+            const G2 nxt = R.pair(k + 2 < N ? k + 2 : 0);
             stepg(r, cur.a0, cur.b0);
             stepg(r, cur.a1, cur.b1);
             transpose_fwd(r, x.next(), L);
             cur = nxt;
         }
-    } else {
-        // beta: j = N..2 twice (:203-230), the second time only down to M
-        G2 cur = R.pair(N - 2);
-        for (int t = 0; t < 2 * N - M; t += 2) {
-            const int j = t < N ? N - t : 2 * N - t;
-            int jn = j - 2;
-            if (jn < 2) jn = N;
-            const G2 nxt = R.pair(jn - 2);
-            if (t >= N && (j == N || ((j - M) & (kWin - 1)) == 0)) {
-                const int w = (j - M + kWin - 1) / kWin - 1;
-                *reinterpret_cast<float4 *>(ckq + (g.nckA + w) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+        // pass 2 up to the crossing point M (a multiple of kWin), checkpoint every kWin steps
+        for (int k = 0; k < M; k += kWin) {
+            *reinterpret_cast<float4 *>(ckq + (k / kWin) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int j = 0; j < kWin; j += 2) {
+                const G2 nxt = R.pair(k + j + 2);          // k + j + 2 <= M < N
+                stepg(r, cur.a0, cur.b0);
+                stepg(r, cur.a1, cur.b1);
+                transpose_fwd(r, x.next(), L);
+                cur = nxt;
             }
+        }
+    } else {
+        // beta pass 1 (:203-213): j = N..2, then beta[N] <- beta[0] (:216-217)
+        G2 cur = R.pair(N - 2);
+#pragma unroll 2
+        for (int j = N; j > 0; j -= 2) {
+            const G2 nxt = R.pair(j >= 4 ? j - 4 : N - 2);
             stepg(r, cur.a1, cur.b1);      // gamma[j-1] (odd)
             stepg(r, cur.a0, cur.b0);      // gamma[j-2] (even)
             transpose_bwd(r, x.next(), L);
             cur = nxt;
+        }
+        // pass 2 down to M: a checkpoint at the end of every alpha-warp window
+        int j = N;
+        const int ragged = (N - M) & (kWin - 1);           // 0 or 4
+        if (ragged) {
+            *reinterpret_cast<float4 *>(ckq + (g.nckA + g.nckB - 1) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            for (int t = 0; t < ragged; t += 2, j -= 2) {
+                const G2 nxt = R.pair(j - 4);
+                stepg(r, cur.a1, cur.b1);
+                stepg(r, cur.a0, cur.b0);
+                transpose_bwd(r, x.next(), L);
+                cur = nxt;
+            }
+        }
+        for (; j > M; j -= kWin) {
+            *reinterpret_cast<float4 *>(ckq + (g.nckA + (j - M) / kWin - 1) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int t = 0; t < kWin; t += 2) {
+                const G2 nxt = R.pair(j - t - 4);           // >= M - 4 >= 4
+                stepg(r, cur.a1, cur.b1);
+                stepg(r, cur.a0, cur.b0);
+                transpose_bwd(r, x.next(), L);
+                cur = nxt;
+            }
         }
     }
     __syncthreads();

@@ -4,7 +4,7 @@
 //
 // results[0] FADD   results[1] FMNMX   results[2] ACS mix (2 FADD + 1 FMNMX)
 // results[3] SHFL   results[4] DADD    results[5] F2F (f64<->f32 conversions)
-// results[6] add.f32x2 (counted as 2 lane-ops)   results[7] SM clock in MHz
+// results[6] add.f32x2 on packed registers (counted as 2 lane-ops)   results[7] SM clock in MHz
 #include "common.cuh"
 
 namespace b200dvb {
@@ -22,6 +22,10 @@ __global__ void __launch_bounds__(1024) probe(float seed, long long *cycles, flo
 #pragma unroll
     for (int i = 0; i < kChains; ++i) { x[i] = seed + i + threadIdx.x; d[i] = x[i]; }
     const float c = seed * 0.5f, c2 = seed * 0.25f;
+    unsigned long long pk[kChains], qk;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(pk[i]) : "f"(x[i]), "f"(x[i] + 1.f));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(qk) : "f"(c));
     __syncthreads();
     const long long t0 = clock64();
     for (int it = 0; it < kIter; ++it) {
@@ -41,20 +45,18 @@ __global__ void __launch_bounds__(1024) probe(float seed, long long *cycles, flo
                 asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(x[i]) : "d"(d[i]));
                 asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[i]) : "f"(x[i]));
             }
-            if (OP == 6) {
-                unsigned long long p, q;
-                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x[i]), "f"(x[(i + 1) % kChains]));
-                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(q) : "f"(c));
-                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(q));
-                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x[i]), "=f"(x[(i + 1) % kChains]) : "l"(p));
-            }
+            if (OP == 6) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(pk[i]) : "l"(qk));
         }
     }
     const long long t1 = clock64();
     __syncthreads();
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < kChains; ++i) acc += x[i] + (float)d[i];
+    for (int i = 0; i < kChains; ++i) {
+        float lo, hi;
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(pk[i]));
+        acc += x[i] + (float)d[i] + lo + hi;
+    }
     if (acc == 123.456f) sink[0] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }

@@ -128,7 +128,7 @@ int b200dvb_map(b200dvb_modem_t modem, size_t n_sym, const uint8_t *bits, void *
                 int out_f64, void *stream);
 /* Max-log bit LLRs, clipped to +-30, positive = bit 1.  Replaces compute_llr
  * (test_sdr_with_coding.py:200-225).  iq float2[n_sym] -> llr float32[n_sym*bps];
- * noise_var is floored at 0.005 (:202).  `scale` multiplies the clipped LLR
+ * noise_var is floored at 0.005 (:202); iq and llr must be 16-byte aligned.  `scale` multiplies the clipped LLR
  * (use -1 to feed the decoder, whose convention is positive = bit 0). */
 int b200dvb_demap(b200dvb_modem_t modem, size_t n_sym, const void *iq, float noise_var,
                   float scale, float *llr, void *stream);

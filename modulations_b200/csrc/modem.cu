@@ -73,34 +73,16 @@ __global__ void hard_kernel(size_t n, int bps, const typename Cplx<InT>::type *_
     }
 }
 
-template <int BPS>
-__device__ __forceinline__ void store_llr(float *__restrict__ out, const float (&v)[BPS])
-{
-    if (BPS == 4) {
-        *reinterpret_cast<float4 *>(out) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (BPS == 8) {
-        *reinterpret_cast<float4 *>(out) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(out + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else if (BPS == 2 || BPS == 6) {
-#pragma unroll
-        for (int b = 0; b < BPS; b += 2) *reinterpret_cast<float2 *>(out + b) = make_float2(v[b], v[b + 1]);
-    } else {
-#pragma unroll
-        for (int b = 0; b < BPS; ++b) out[b] = v[b];
-    }
-}
-
-template <int BPS>
-__global__ void __launch_bounds__(kThreads)
-demap_generic(size_t n, const float2 *__restrict__ iq, const float *__restrict__ table,
-              float inv_nv, float scale, float *__restrict__ llr)
-{
-    constexpr int M = 1 << BPS;
-    __shared__ float2 tab[M];
-    for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = make_float2(table[2 * i], table[2 * i + 1]);
-    __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float2 s = __ldcs(iq + i);
+// ---- soft demapper ---------------------------------------------------------------
+// One thread computes SPT consecutive symbols (8*SPT bytes in, 4*SPT*BPS bytes out).
+// When a thread's output chunk is exactly 16 bytes the float4 stores of a warp are
+// already contiguous; larger chunks are staged through shared memory so that every
+// global store instruction of a warp still writes 512 contiguous bytes.
+template <int BPS> struct GenericLlr {
+    const float2 *tab;          // shared memory
+    float inv_nv, scale;
+    __device__ __forceinline__ void operator()(const float2 s, float (&v)[BPS]) const {
+        constexpr int M = 1 << BPS;
         float d0[BPS], d1[BPS];
 #pragma unroll
         for (int b = 0; b < BPS; ++b) { d0[b] = 3.0e38f; d1[b] = 3.0e38f; }
@@ -114,37 +96,138 @@ demap_generic(size_t n, const float2 *__restrict__ iq, const float *__restrict__
                 else                          d0[b] = fminf(d0[b], d);
             }
         }
-        float v[BPS];
 #pragma unroll
         for (int b = 0; b < BPS; ++b)
             v[b] = fminf(fmaxf((d0[b] - d1[b]) * inv_nv, -30.f), 30.f) * scale;
-        store_llr<BPS>(llr + i * BPS, v);
     }
-}
+};
 
-// Per-axis piecewise-linear demapper.  coef: float2[2][HALF][nseg].
-template <int HALF>
-__global__ void __launch_bounds__(kThreads)
-demap_pwl(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
-          float x0a, float invda, float x0b, float invdb, int first_is_q, float inv_nv, float scale,
-          float *__restrict__ llr)
-{
-    extern __shared__ float2 sc[];
-    for (int i = threadIdx.x; i < 2 * HALF * nseg; i += blockDim.x) sc[i] = coef[i];
-    __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float2 s = __ldcs(iq + i);
+template <int BPS> struct PwlLlr {          // BPS = 2 * HALF
+    const float2 *sc;           // shared memory: float2[2][HALF][nseg]
+    int nseg, first_is_q;
+    float x0a, invda, x0b, invdb, inv_nv, scale;
+    __device__ __forceinline__ void operator()(const float2 s, float (&v)[BPS]) const {
+        constexpr int HALF = BPS / 2;
         const float xa = first_is_q ? s.y : s.x, xb = first_is_q ? s.x : s.y;
         const int ua = min(max(__float2int_rd((xa - x0a) * invda), 0), nseg - 1);
         const int ub = min(max(__float2int_rd((xb - x0b) * invdb), 0), nseg - 1);
-        float v[2 * HALF];
 #pragma unroll
         for (int b = 0; b < HALF; ++b) {
             const float2 ca = sc[b * nseg + ua], cb = sc[(HALF + b) * nseg + ub];
             v[b] = fminf(fmaxf(fmaf(ca.x, xa, ca.y) * inv_nv, -30.f), 30.f) * scale;
             v[HALF + b] = fminf(fmaxf(fmaf(cb.x, xb, cb.y) * inv_nv, -30.f), 30.f) * scale;
         }
-        store_llr<2 * HALF>(llr + i * 2 * HALF, v);
+    }
+};
+
+template <int BPS, int SPT, class F>
+__device__ __forceinline__ void demap_body(size_t n, const float2 *__restrict__ iq, float *__restrict__ llr,
+                                           const F &f, float *stage)
+{
+    constexpr int CH = BPS * SPT;                       // floats per thread
+    constexpr bool kStage = (CH != 4);
+    const size_t tile = (size_t)blockDim.x * SPT;       // symbols per block iteration
+    for (size_t base = (size_t)blockIdx.x * tile; base < n; base += (size_t)gridDim.x * tile) {
+        const size_t i0 = base + (size_t)threadIdx.x * SPT;
+        const bool full = base + tile <= n;
+        float2 s[SPT];
+        if (full && (SPT % 2) == 0) {
+#pragma unroll
+            for (int j = 0; j < SPT; j += 2) {
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(iq + i0 + j));
+                s[j] = make_float2(t.x, t.y); s[j + 1] = make_float2(t.z, t.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPT; ++j) s[j] = (i0 + j < n) ? __ldcs(iq + i0 + j) : make_float2(0.f, 0.f);
+        }
+        float v[SPT][BPS];
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) f(s[j], v[j]);
+        if (!kStage) {
+            if (full || i0 + SPT <= n) {
+                const float *p = &v[0][0];
+                __stcs(reinterpret_cast<float4 *>(llr + i0 * BPS), make_float4(p[0], p[1], p[2], p[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < SPT; ++j)
+#pragma unroll
+                    for (int b = 0; b < BPS; ++b)
+                        if (i0 + j < n) llr[(i0 + j) * BPS + b] = v[j][b];
+            }
+        } else {
+            float *mine = stage + threadIdx.x * CH;
+#pragma unroll
+            for (int j = 0; j < SPT; ++j)
+#pragma unroll
+                for (int b = 0; b < BPS; ++b) mine[j * BPS + b] = v[j][b];
+            __syncthreads();
+            const size_t remain = (n - base) * BPS;                         // floats left from `base`
+            const size_t tot = remain < (size_t)blockDim.x * CH ? remain : (size_t)blockDim.x * CH;
+            float *out = llr + base * BPS;                                   // 16-byte aligned: tile*BPS % 4 == 0
+            for (size_t q = threadIdx.x; q * 4 + 3 < tot; q += blockDim.x)
+                __stcs(reinterpret_cast<float4 *>(out) + q, reinterpret_cast<const float4 *>(stage)[q]);
+            for (size_t q = (tot / 4) * 4 + threadIdx.x; q < tot; q += blockDim.x) out[q] = stage[q];
+            __syncthreads();
+        }
+    }
+}
+
+template <int BPS, int SPT>
+__global__ void __launch_bounds__(kThreads)
+demap_generic(size_t n, const float2 *__restrict__ iq, const float *__restrict__ table,
+              float inv_nv, float scale, float *__restrict__ llr)
+{
+    constexpr int M = 1 << BPS;
+    __shared__ float2 tab[M];
+    __shared__ __align__(16) float stage[(BPS * SPT != 4) ? kThreads * BPS * SPT : 4];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = make_float2(table[2 * i], table[2 * i + 1]);
+    __syncthreads();
+    GenericLlr<BPS> f{tab, inv_nv, scale};
+    demap_body<BPS, SPT>(n, iq, llr, f, stage);
+}
+
+// Per-axis piecewise-linear demapper.  coef: float2[2][HALF][nseg].
+template <int HALF, int SPT>
+__global__ void __launch_bounds__(kThreads)
+demap_pwl(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
+          float x0a, float invda, float x0b, float invdb, int first_is_q, float inv_nv, float scale,
+          float *__restrict__ llr)
+{
+    constexpr int BPS = 2 * HALF;
+    __shared__ float2 sc[2 * 4 * 30];
+    __shared__ __align__(16) float stage[(BPS * SPT != 4) ? kThreads * BPS * SPT : 4];
+    for (int i = threadIdx.x; i < 2 * HALF * nseg; i += blockDim.x) sc[i] = coef[i];
+    __syncthreads();
+    PwlLlr<BPS> f{sc, nseg, first_is_q, x0a, invda, x0b, invdb, inv_nv, scale};
+    demap_body<BPS, SPT>(n, iq, llr, f, stage);
+}
+
+// 256QAM (4 bits per axis): one thread per (symbol, axis) writes one float4, so a warp's
+// stores are 512 contiguous bytes with no staging; both threads of a symbol read the same
+// 8 input bytes.
+__global__ void __launch_bounds__(kThreads)
+demap_pwl_axis4(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
+                float x0a, float invda, float x0b, float invdb, int first_is_q, float inv_nv, float scale,
+                float4 *__restrict__ llr4)
+{
+    __shared__ float2 sc[2 * 4 * 30];
+    for (int i = threadIdx.x; i < 2 * 4 * nseg; i += blockDim.x) sc[i] = coef[i];
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += (size_t)gridDim.x * blockDim.x) {
+        const float2 s = __ldcs(iq + (t >> 1));
+        const int ax = (int)(t & 1);                    // 0: first half of the label, 1: second half
+        const float x = (ax ^ first_is_q) ? s.y : s.x;
+        const float x0 = ax ? x0b : x0a, invd = ax ? invdb : invda;
+        const int u = min(max(__float2int_rd((x - x0) * invd), 0), nseg - 1);
+        const float2 *c = sc + ax * 4 * nseg + u;
+        float v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float2 cc = c[b * nseg];
+            v[b] = fminf(fmaxf(fmaf(cc.x, x, cc.y) * inv_nv, -30.f), 30.f) * scale;
+        }
+        __stcs(llr4 + t, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -234,31 +317,37 @@ int launch_demap(const Modem &m, size_t n, const void *iq_, float noise_var, flo
 {
     if (n == 0) return B200DVB_OK;
     const float2 *iq = (const float2 *)iq_;
+    if ((reinterpret_cast<uintptr_t>(iq_) & 15) || (reinterpret_cast<uintptr_t>(llr) & 15))
+        return B200DVB_EINVAL;                               // vector loads/stores need 16-byte alignment
     const float nv = noise_var > 0.005f ? noise_var : 0.005f;      // test_sdr_with_coding.py:202
     const float inv_nv = 1.0f / nv;
-    const int grid = grid_for(n, kThreads, 8);
     if (m.pwl) {
         const float2 *coef = (const float2 *)m.d_pwl;
-        const size_t sm = (size_t)2 * m.half * m.nseg * sizeof(float2);
         const int fq = (m.separable == 2);
-#define PWL(H) demap_pwl<H><<<grid, kThreads, sm, s>>>(n, iq, coef, m.nseg, m.pwl_x0[0], m.pwl_invd[0], \
-                                                       m.pwl_x0[1], m.pwl_invd[1], fq, inv_nv, scale, llr)
+#define PWL(H, S) demap_pwl<H, S><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(                    \
+        n, iq, coef, m.nseg, m.pwl_x0[0], m.pwl_invd[0], m.pwl_x0[1], m.pwl_invd[1], fq, inv_nv, scale, llr)
         switch (m.half) {
-        case 1: PWL(1); break;
-        case 2: PWL(2); break;
-        case 3: PWL(3); break;
-        case 4: PWL(4); break;
+        case 1: PWL(1, 2); break;
+        case 2: PWL(2, 1); break;
+        case 3: PWL(3, 2); break;
+        case 4:
+            demap_pwl_axis4<<<grid_for(2 * n, kThreads, 8), kThreads, 0, s>>>(
+                n, iq, coef, m.nseg, m.pwl_x0[0], m.pwl_invd[0], m.pwl_x0[1], m.pwl_invd[1], fq, inv_nv, scale,
+                reinterpret_cast<float4 *>(llr));
+            break;
         default: return B200DVB_ENOSPEC;
         }
 #undef PWL
     } else {
         switch (m.bps) {
-        case 1: demap_generic<1><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
-        case 2: demap_generic<2><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
-        case 3: demap_generic<3><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
-        case 4: demap_generic<4><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
-        case 6: demap_generic<6><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
-        case 8: demap_generic<8><<<grid, kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr); break;
+#define GEN(B, S) demap_generic<B, S><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr)
+        case 1: GEN(1, 4); break;
+        case 2: GEN(2, 2); break;
+        case 3: GEN(3, 4); break;
+        case 4: GEN(4, 1); break;
+        case 6: GEN(6, 2); break;
+        case 8: GEN(8, 1); break;
+#undef GEN
         default: return B200DVB_ENOSPEC;
         }
     }

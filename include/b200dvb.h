@@ -161,6 +161,10 @@ int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
  * recursion-out + extrinsic, epilogue, hard decision, CTA total, 0, 0}. */
 int b200dvb_debug_phase_cycles(double *out8_h, int reset);
 
+/* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the
+ * two warps of a lane quadrant, as the decoder uses it; *errors_h = mismatching words. */
+int b200dvb_tmem_selftest(int *errors_h);
+
 /* Small device-throughput probes used by bench.py to state the ALU roofline
  * (FADD / FMNMX / SHFL lane-ops per clock per SM).  results_h: double[8]. */
 int b200dvb_microbench(double *results_h);

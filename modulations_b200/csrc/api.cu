@@ -347,6 +347,12 @@ int b200dvb_debug_phase_cycles(double *out8_h, int reset)
     return read_phase_cycles(out8_h, reset);
 }
 
+int b200dvb_tmem_selftest(int *errors_h)
+{
+    if (!errors_h) return B200DVB_EINVAL;
+    return run_tmem_selftest(errors_h);
+}
+
 int b200dvb_microbench(double *results_h)
 {
     if (!results_h) return B200DVB_EINVAL;

@@ -97,5 +97,6 @@ int launch_hard(const Modem &m, size_t n, const void *iq, int in_f64, uint8_t *b
 
 int modem_build_pwl(Modem &m);
 int run_microbench(double *results_h);
+int run_tmem_selftest(int *result_h);
 
 }  // namespace b200dvb

@@ -105,3 +105,79 @@ int run_microbench(double *r)
 }
 
 }  // namespace b200dvb
+
+// ---------------------------------------------------------------------------
+// TMEM as a lane-private scratchpad shared by the warps of one lane quadrant:
+// self-test of the tcgen05 alloc / st / ld / dealloc protocol the decoder uses for
+// its recursion checkpoints (warps w and w+4 address the same 32 TMEM lanes).
+// ---------------------------------------------------------------------------
+namespace b200dvb {
+namespace {
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__global__ void __launch_bounds__(256) tmem_selftest_kernel(int ncols, int *errors)
+{
+    __shared__ unsigned s_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_base)), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned base = s_base;
+    const unsigned quad = (unsigned)(warp & 3) * 32u;
+    if (warp >= 4) {                                   // writers
+        for (int c = 0; c < ncols; c += 4) {
+            const unsigned v0 = (quad + lane) * 1000u + c, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3;
+            const unsigned taddr = base + (quad << 16) + c;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(taddr), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    int bad = 0;
+    if (warp < 4) {                                    // readers in the same quadrant
+        for (int c = 0; c < ncols; c += 4) {
+            unsigned r0, r1, r2, r3;
+            const unsigned taddr = base + (quad << 16) + c;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;");
+            const unsigned e = (quad + lane) * 1000u + c;
+            bad += (r0 != e) + (r1 != e + 1) + (r2 != e + 2) + (r3 != e + 3);
+        }
+    }
+    if (bad) atomicAdd(errors, bad);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols));
+}
+
+}  // namespace
+
+int run_tmem_selftest(int *result_h)
+{
+    int *d = nullptr;
+    B2_CUDA(cudaMalloc(&d, sizeof(int)));
+    B2_CUDA(cudaMemset(d, 0, sizeof(int)));
+    int sms = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    tmem_selftest_kernel<<<sms, 256>>>(512, d);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(cudaMemcpy(result_h, d, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return B200DVB_OK;
+}
+
+}  // namespace b200dvb

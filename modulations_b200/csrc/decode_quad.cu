@@ -155,6 +155,46 @@ __device__ __forceinline__ void transpose_bwd(float (&r)[4], float *xb, const La
     r[0] = xb[L.xr]; r[2] = xb[L.xr + 4]; r[1] = xb[L.xr + 8]; r[3] = xb[L.xr + 12];
 }
 
+// Recursion checkpoints (one float4 per lane): in shared memory, or — when that frees
+// enough room for a fourth group of frames — in tensor memory.  TMEM is lane-private,
+// but the alpha and beta warp of a group sit in the same lane quadrant (warp ids g and
+// g + 4), so lane l of one reads what lane l of the other wrote (tcgen05.st/ld .32x32b).
+template <bool TMEM> struct Ckpt;
+template <> struct Ckpt<false> {
+    float *base;                                   // this lane's float4 slot of checkpoint 0
+    __device__ __forceinline__ void store(int idx, const float (&r)[4]) const {
+        *reinterpret_cast<float4 *>(base + idx * 16) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    __device__ __forceinline__ void load(int idx, float (&r)[4]) const {
+        const float4 c = *reinterpret_cast<const float4 *>(base + idx * 16);
+        r[0] = c.x; r[1] = c.y; r[2] = c.z; r[3] = c.w;
+    }
+    __device__ __forceinline__ void publish() const {}
+    __device__ __forceinline__ void acquire() const {}
+};
+template <> struct Ckpt<true> {
+    unsigned taddr;                                // TMEM address of column 0 in this warp's lane quadrant
+    __device__ __forceinline__ void store(int idx, const float (&r)[4]) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(taddr + 4u * idx), "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])),
+                       "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])) : "memory");
+    }
+    __device__ __forceinline__ void load(int idx, float (&r)[4]) const {
+        unsigned a, b, c, d;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr + 4u * idx) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        r[0] = __uint_as_float(a); r[1] = __uint_as_float(b); r[2] = __uint_as_float(c); r[3] = __uint_as_float(d);
+    }
+    __device__ __forceinline__ void publish() const {      // before the CTA barrier that hands checkpoints over
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __device__ __forceinline__ void acquire() const {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+};
+
 struct Xch {            // two alternating exchange buffers: one __syncwarp per use
     float *b0, *b1;
     __device__ __forceinline__ float *next() { float *t = b0; b0 = b1; b1 = t; return t; }
@@ -226,15 +266,12 @@ __device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], const GH 
 // Branch metrics are always loaded one step (or one step pair) ahead of their use:
 // the exchange-buffer stores in between would otherwise pin the loads behind them.
 // ---------------------------------------------------------------------------
-template <int LEN>
+template <int LEN, class CK>
 __device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const Recs &R,
-                                             const float *ck, int j0, const Lane &L, Xch &x)
+                                             const CK &ck, int ck_idx, int j0, const Lane &L, Xch &x)
 {
     float wb[LEN][4];
-    {
-        const float4 c = *reinterpret_cast<const float4 *>(ck);
-        wb[LEN - 1][0] = c.x; wb[LEN - 1][1] = c.y; wb[LEN - 1][2] = c.z; wb[LEN - 1][3] = c.w;
-    }
+    ck.load(ck_idx, wb[LEN - 1]);
     float2 gA, gB, nA, nB;
     R.template one<(LEN - 1) & 1>(j0 + LEN - 1, gA, gB);
 #pragma unroll
@@ -265,14 +302,12 @@ __device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const R
     }
 }
 
+template <class CK>
 __device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Recs &R,
-                                            const float *ck, int j0, const Lane &L, Xch &x)
+                                            const CK &ck, int ck_idx, int j0, const Lane &L, Xch &x)
 {
     float wa[kWin][4];
-    {
-        const float4 c = *reinterpret_cast<const float4 *>(ck);
-        wa[0][0] = c.x; wa[0][1] = c.y; wa[0][2] = c.z; wa[0][3] = c.w;
-    }
+    ck.load(ck_idx, wa[0]);
     float2 gA, gB, nA, nB;
     R.template one<0>(j0, gA, gB);
 #pragma unroll
@@ -303,13 +338,13 @@ __device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Re
     }
 }
 
-__device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *ckbuf, float *xch,
-                                          int warp, int wid, const Lane &L, long long &t_mid)
+template <class CK>
+__device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const CK &ck, float *xch,
+                                          int warp, int xslot, const Lane &L, long long &t_mid)
 {
     const int N = g.N, M = g.M;
     float *grec = gam + L.q * g.rec_stride;
-    float *ckq = ckbuf + L.q * g.ck_stride + 4 * L.p;     // this lane's float4 slot, checkpoint 0
-    Xch x{xch + wid * 2 * kXchFloats, xch + wid * 2 * kXchFloats + kXchFloats};
+    Xch x{xch + xslot * 2 * kXchFloats, xch + xslot * 2 * kXchFloats + kXchFloats};
     Recs R;
     R.pA0 = grec + L.oA[0];     R.pB0 = grec + L.oB[0];
     R.pA1 = grec + 8 + L.oA[1]; R.pB1 = grec + 8 + L.oB[1];
@@ -329,7 +364,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *
         }
         // pass 2 up to the crossing point M (a multiple of kWin), checkpoint every kWin steps
         for (int k = 0; k < M; k += kWin) {
-            *reinterpret_cast<float4 *>(ckq + (k / kWin) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            ck.store(k / kWin, r);
 #pragma unroll
             for (int j = 0; j < kWin; j += 2) {
                 const G2 nxt = R.pair(k + j + 2);          // k + j + 2 <= M < N
@@ -354,7 +389,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *
         int j = N;
         const int ragged = (N - M) & (kWin - 1);           // 0 or 4
         if (ragged) {
-            *reinterpret_cast<float4 *>(ckq + (g.nckA + g.nckB - 1) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            ck.store(g.nckA + g.nckB - 1, r);
             for (int t = 0; t < ragged; t += 2, j -= 2) {
                 const G2 nxt = R.pair(j - 4);
                 stepg(r, cur.a1, cur.b1);
@@ -364,7 +399,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *
             }
         }
         for (; j > M; j -= kWin) {
-            *reinterpret_cast<float4 *>(ckq + (g.nckA + (j - M) / kWin - 1) * 16) = make_float4(r[0], r[1], r[2], r[3]);
+            ck.store(g.nckA + (j - M) / kWin - 1, r);
 #pragma unroll
             for (int t = 0; t < kWin; t += 2) {
                 const G2 nxt = R.pair(j - t - 4);           // >= M - 4 >= 4
@@ -375,18 +410,19 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, float *
             }
         }
     }
+    ck.publish();
     __syncthreads();
+    ck.acquire();
     t_mid = clock64();
     if (warp == 0) {
         for (int w = 0; w < g.nckB; ++w) {
             const int j0 = M + w * kWin;
-            const float *ck = ckq + (g.nckA + w) * 16;
-            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, R, ck, j0, L, x);
-            else                window_alpha<4>(r, grec, R, ck, j0, L, x);
+            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, R, ck, g.nckA + w, j0, L, x);
+            else                window_alpha<4>(r, grec, R, ck, g.nckA + w, j0, L, x);
         }
     } else {
         for (int w = g.nckA - 1; w >= 0; --w)
-            window_beta(r, grec, R, ckq + w * 16, w * kWin, L, x);
+            window_beta(r, grec, R, ck, w, w * kWin, L, x);
     }
     __syncthreads();
 }
@@ -435,7 +471,7 @@ __device__ __forceinline__ double2 make_extrinsic(const float4 uv, double YA, do
     return make_double2(ea, eb);
 }
 
-template <bool SISO_ONLY>
+template <bool SISO_ONLY, bool TMEM>
 __global__ void __launch_bounds__(kMaxCtaThreads)
 quad_kernel(const QuadArgs A)
 {
@@ -445,21 +481,40 @@ quad_kernel(const QuadArgs A)
     const int tid = threadIdx.x, lane = tid & 31;
     const int NT = blockDim.x;                       // recursion warps + helper warps (prep / epilogue only)
     const int wid = tid >> 5;
-    const bool helper = wid >= 2 * g.groups;         // helper warps only take part in the data-parallel phases
-    const int warp = wid >= g.groups;                // 0: forward (alpha) warps, 1: backward (beta) warps
-    const int wgrp = helper ? 0 : (warp ? wid - g.groups : wid);   // 8-frame group this warp serves
+    // warp roles.  smem checkpoints: alpha warps 0..G-1, beta warps G..2G-1.  TMEM checkpoints
+    // (G <= 4): alpha warp g and beta warp 4+g share lane quadrant g.  Everything else helps
+    // with the data-parallel phases only.
+    const int bfirst = TMEM ? 4 : g.groups;
+    const bool isA = wid < g.groups, isB = wid >= bfirst && wid < bfirst + g.groups;
+    const bool helper = !(isA || isB);
+    const int warp = isB;                            // 0: forward (alpha) warps, 1: backward (beta) warps
+    const int wgrp = helper ? 0 : (isB ? wid - bfirst : wid);      // 8-frame group this warp serves
+    const int xslot = helper ? 0 : (isB ? g.groups + wgrp : wgrp); // exchange-buffer slot
     // ---- shared memory carve-up -------------------------------------------------
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((7 * N * 2 + 15) / 16) * 16;
     float *gam = reinterpret_cast<float *>(smem_raw + tab_bytes);
     const int FR = g.frames;                         // frames this CTA decodes at a time
-    const int areas = FR + ((FR & 7) != 0);          // idle quads (frame slot >= FR) share one scratch area
+    const int areas = FR + (FR < 8 * g.groups);      // idle quads (frame slot >= FR) share one scratch area
     float *ckbuf = gam + areas * g.rec_stride;
-    float *xch = ckbuf + areas * g.ck_stride;
+    float *xch = ckbuf + (TMEM ? 0 : areas * g.ck_stride);
     int *flags = reinterpret_cast<int *>(xch + 4 * g.groups * kXchFloats);
-    unsigned char *hb = reinterpret_cast<unsigned char *>(flags + 64);   // [8][N] hard-bit pairs
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(flags + 64);
+    unsigned char *hb = reinterpret_cast<unsigned char *>(gam);   // hard-bit pairs: the records are dead by then
+    if (TMEM && wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TMEM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // [8][N] hard-bit pairs
 
     for (int i = tid; i < 7 * N; i += NT) tab[i] = A.tab[i];
+    __syncthreads();
+    unsigned tmem_base = 0;
+    if (TMEM) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_base = *tmem_slot;
+    }
     const int P = FR * N;                   // (frame, step) positions of this CTA, dealt out flat
     const unsigned magic = g.magic;
     const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
@@ -553,7 +608,10 @@ quad_kernel(const QuadArgs A)
             const long long t1 = clock64();
             long long t2;
             if (!helper) {
-                siso_core(g, gam, ckbuf, xch, warp, wid, L, t2);
+                Ckpt<TMEM> ck;
+                if constexpr (TMEM) ck.taddr = tmem_base + (((unsigned)(wid & 3) * 32u) << 16);
+                else ck.base = ckbuf + L.q * g.ck_stride + 4 * L.p;
+                siso_core(g, gam, ck, xch, warp, xslot, L, t2);
             } else {
                 __syncthreads();
                 t2 = clock64();
@@ -674,6 +732,12 @@ quad_kernel(const QuadArgs A)
             }
         }
     }
+    if (TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (wid == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+    }
 }
 
 }  // namespace
@@ -683,10 +747,11 @@ quad_kernel(const QuadArgs A)
 // ---------------------------------------------------------------------------
 static size_t quad_smem_bytes(const QuadGeom &g)
 {
-    const int areas = g.frames + ((g.frames & 7) != 0);
+    const int areas = g.frames + (g.frames < 8 * g.groups);
     size_t tab = ((size_t)7 * g.N * 2 + 15) / 16 * 16;
-    size_t fl = (size_t)areas * g.rec_stride + (size_t)areas * g.ck_stride + 4 * g.groups * kXchFloats;
-    return tab + fl * 4 + 64 * 4 + (size_t)g.frames * g.N;
+    size_t fl = (size_t)areas * g.rec_stride + (g.use_tmem ? 0 : (size_t)areas * g.ck_stride) +
+                4 * g.groups * kXchFloats;
+    return tab + fl * 4 + 68 * 4;
 }
 
 int quad_configure(Codec &c)
@@ -710,24 +775,36 @@ int quad_configure(Codec &c)
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
     c.num_sms = prop.multiProcessorCount;
-    // One CTA per SM when possible: `groups` pairs of (alpha warp, beta warp), 8 frames per
-    // pair, all warps in the same phase so they share the instruction cache.  Fall back to
-    // fewer groups, then to fewer frames in a single group (8, 4, 2, 1), as N grows.
+    // One CTA per SM: `groups` pairs of (alpha warp, beta warp), 8 frames per pair, all warps
+    // in the same phase so they share the instruction cache.  Two placements of the recursion
+    // checkpoints are tried and the one that keeps more frames resident wins: shared memory
+    // (up to 7 groups when N is small) or tensor memory (up to 4 groups: one per lane quadrant).
+    const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
     const int want_groups = getenv("B200DVB_GROUPS") ? atoi(getenv("B200DVB_GROUPS")) : kMaxGroups;
-    bool ok = false;
-    for (g.groups = want_groups < 1 ? 1 : (want_groups > kMaxGroups ? kMaxGroups : want_groups); g.groups >= 1 && !ok; --g.groups) {
-        g.frames = 8 * g.groups;
-        g.smem_bytes = quad_smem_bytes(g);
-        if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) { ok = true; break; }
-    }
-    if (!ok) {
-        g.groups = 1;
-        for (g.frames = 4; g.frames >= 1; g.frames >>= 1) {
-            g.smem_bytes = quad_smem_bytes(g);
-            if (g.smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) { ok = true; break; }
+    const int force_tmem = getenv("B200DVB_TMEM") ? atoi(getenv("B200DVB_TMEM")) : -1;
+    QuadGeom best{};
+    best.frames = 0;
+    for (int tm = 0; tm < 2; ++tm) {
+        if (force_tmem >= 0 && tm != force_tmem) continue;
+        QuadGeom t = g;
+        t.use_tmem = tm;
+        t.tmem_cols = 32;
+        while (t.tmem_cols < 4 * (t.nckA + t.nckB)) t.tmem_cols *= 2;
+        if (tm && t.tmem_cols > 512) continue;
+        const int gmax = tm ? 4 : kMaxGroups;
+        int gr = want_groups < 1 ? 1 : (want_groups > gmax ? gmax : want_groups);
+        bool ok = false;
+        for (; gr >= 1 && !ok; --gr) {
+            t.groups = gr;
+            for (t.frames = 8 * gr; t.frames > 8 * (gr - 1) && t.frames >= 1; --t.frames) {
+                t.smem_bytes = quad_smem_bytes(t);
+                if (t.smem_bytes <= cap) { ok = true; break; }
+            }
         }
+        if (ok && t.frames > best.frames) best = t;
     }
-    if (!ok) return B200DVB_ENOSPEC;
+    if (best.frames < 1) return B200DVB_ENOSPEC;
+    g = best;
     {
         const char *e = getenv("B200DVB_THREADS");
         int t = e ? atoi(e) : kMaxCtaThreads;
@@ -736,10 +813,18 @@ int quad_configure(Codec &c)
         if (t > kMaxCtaThreads) t = kMaxCtaThreads;
         g.threads = t;
     }
-    B2_CUDA(cudaFuncSetAttribute(quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    B2_CUDA(cudaFuncSetAttribute(quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(quad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     int occ = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false>, g.threads, g.smem_bytes));
+    if (g.use_tmem) {
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false, true>, g.threads, g.smem_bytes));
+        if (occ > 1 && g.tmem_cols > 256) occ = 1;      // two CTAs must both get their TMEM columns
+        if (occ > 512 / g.tmem_cols) occ = 512 / g.tmem_cols;
+    } else {
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_kernel<false, false>, g.threads, g.smem_bytes));
+    }
     if (occ < 1) return B200DVB_ENOSPEC;
     g.ctas_per_sm = occ;
     return B200DVB_OK;
@@ -785,7 +870,8 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
     A.vec_wy = even && c.vec_wy;
     A.Le1 = reinterpret_cast<double2 *>(align256(ws));
     A.Le2 = A.Le1 + per; A.Y = A.Le2 + per;
-    quad_kernel<false><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
+    if (c.geom.use_tmem) quad_kernel<false, true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
+    else                 quad_kernel<false, false><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }
@@ -805,7 +891,8 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
     A.LeA = Le_A; A.LeB = Le_B; A.siso_sf = sf;
     A.Y = reinterpret_cast<double2 *>(align256(ws));
     A.Le1 = A.Y; A.Le2 = A.Y;
-    quad_kernel<true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
+    if (c.geom.use_tmem) quad_kernel<true, true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
+    else                 quad_kernel<true, false><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

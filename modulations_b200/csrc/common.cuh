@@ -39,6 +39,7 @@ struct QuadGeom {
     int threads;      // CTA size: 64 * groups recursion threads + helper warps
     int use_tmem;     // recursion checkpoints live in tensor memory instead of shared memory
     int tmem_cols;    // TMEM columns allocated per CTA (power of two >= 32)
+    int y_slots;      // > 0: Y = Lc + La is parked in TMEM, this many positions per thread
     int frames;       // frames per CTA (8 * groups, or 4/2/1 when even one group does not fit)
     int ctas_per_sm;
     size_t smem_bytes;

@@ -515,6 +515,11 @@ quad_kernel(const QuadArgs A)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_base = *tmem_slot;
     }
+    // Y = Lc + La (float64) of a thread's own positions lives in its TMEM lane between prep and
+    // epilogue; the four warps of a lane quadrant use disjoint column ranges.
+    const bool YTMEM = TMEM && g.y_slots > 0;
+    const unsigned ytaddr = tmem_base + (((unsigned)(wid & 3) * 32u) << 16) +
+                            4u * (g.nckA + g.nckB) + 4u * g.y_slots * (unsigned)(wid >> 2);
     const int P = FR * N;                   // (frame, step) positions of this CTA, dealt out flat
     const unsigned magic = g.magic;
     const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
@@ -549,7 +554,8 @@ quad_kernel(const QuadArgs A)
             // ---- prep: gather, a-priori add, branch-metric records ------------------
             // kBatch positions per thread are loaded before any is consumed, so the
             // dependent smem-index -> L2 gather round trips overlap.
-            for (int i0 = tid; i0 < P; i0 += kBatch * NT) {
+            for (int it = 0; it * kBatch * NT < P; ++it) {       // warp-uniform trip count
+                const int i0 = tid + it * kBatch * NT;
                 float sA[kBatch], sB[kBatch], pW[kBatch], pY[kBatch];
                 double2 La[kBatch];
 #pragma unroll
@@ -600,10 +606,15 @@ quad_kernel(const QuadArgs A)
                         float *rec = gam + f * g.rec_stride + k * 8;
                         *reinterpret_cast<float4 *>(rec) = lo4;
                         *reinterpret_cast<float4 *>(rec + 4) = hi4;
-                        __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
+                        if (!YTMEM) __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
                     }
+                    if (YTMEM)          // Y stays on chip: this thread's TMEM lane, slot = it*kBatch + u
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(ytaddr + 4u * (it * kBatch + u)), "r"(__double2loint(YA)), "r"(__double2hiint(YA)),
+                                       "r"(__double2loint(YB)), "r"(__double2hiint(YB)) : "memory");
                 }
             }
+            if (YTMEM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             __syncthreads();
             const long long t1 = clock64();
             long long t2;
@@ -619,7 +630,8 @@ quad_kernel(const QuadArgs A)
             }
             const long long t3 = clock64();
             // ---- epilogue: extrinsic LLRs (float64) ---------------------------------
-            for (int i0 = tid; i0 < P; i0 += kBatch * NT) {
+            for (int it = 0; it * kBatch * NT < P; ++it) {
+                const int i0 = tid + it * kBatch * NT;
                 double2 Y[kBatch];
                 float4 uv[kBatch];
 #pragma unroll
@@ -627,8 +639,15 @@ quad_kernel(const QuadArgs A)
                     int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
                     Y[u] = make_double2(0.0, 0.0); uv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i < P && frame0 + f < A.B) {
-                        Y[u] = __ldcg(Yb + (size_t)f * N + k);
+                        if (!YTMEM) Y[u] = __ldcg(Yb + (size_t)f * N + k);
                         uv[u] = *reinterpret_cast<const float4 *>(gam + f * g.rec_stride + k * 8);
+                    }
+                    if (YTMEM) {
+                        int a, b, c, d;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(ytaddr + 4u * (it * kBatch + u)) : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        Y[u] = make_double2(__hiloint2double(b, a), __hiloint2double(d, c));
                     }
                 }
 #pragma unroll
@@ -789,6 +808,7 @@ int quad_configure(Codec &c)
         QuadGeom t = g;
         t.use_tmem = tm;
         t.tmem_cols = 32;
+        t.y_slots = 0;
         while (t.tmem_cols < 4 * (t.nckA + t.nckB)) t.tmem_cols *= 2;
         if (tm && t.tmem_cols > 512) continue;
         const int gmax = tm ? 4 : kMaxGroups;
@@ -805,6 +825,7 @@ int quad_configure(Codec &c)
     }
     if (best.frames < 1) return B200DVB_ENOSPEC;
     g = best;
+    const bool want_y = !getenv("B200DVB_YTMEM") || atoi(getenv("B200DVB_YTMEM"));
     {
         const char *e = getenv("B200DVB_THREADS");
         int t = e ? atoi(e) : kMaxCtaThreads;
@@ -812,6 +833,17 @@ int quad_configure(Codec &c)
         if (t < kCtaThreads * g.groups) t = kCtaThreads * g.groups;
         if (t > kMaxCtaThreads) t = kMaxCtaThreads;
         g.threads = t;
+    }
+    if (g.use_tmem && want_y) {
+        // 4 words per position, ceil(P / threads) positions per thread, 4 warps per lane quadrant
+        const int slots = (g.frames * N + g.threads - 1) / g.threads;
+        const int slots4 = ((slots + kBatch - 1) / kBatch) * kBatch;
+        const int warps_per_quadrant = (g.threads / 32 + 3) / 4;
+        const int need = 4 * (g.nckA + g.nckB) + 4 * slots4 * warps_per_quadrant;
+        if (need <= 512) {
+            g.y_slots = slots4;
+            while (g.tmem_cols < need) g.tmem_cols *= 2;
+        }
     }
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     B2_CUDA(cudaFuncSetAttribute(quad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));

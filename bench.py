@@ -206,8 +206,17 @@ def run_ours(args, rank, world, local_rank):
     avg_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = B * ACS_PER_FRAME / avg_kernel_s / 1e12          # T ACS/s on this GPU
     peak = NOMINAL_ACS_PER_CLK_SM * sms * f_nom / 1e12
+    traffic = None
+    try:        # DRAM bytes of this kernel from the committed `ncu --set full` capture, scaled per frame
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tr["quad_bytes_per_frame"] * B
+    except Exception:
+        pass
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_quad_ncu.txt: 8 373 B/frame at 65 536 "
+                            "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
+                            "reference bits in)",
             "note": "ACS = add-compare-select of the reference algorithm (320*N per SISO, SURVEY 8d); peak = "
                     "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at "
                     "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). HBM traffic of the kernel "

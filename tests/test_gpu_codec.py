@@ -188,3 +188,43 @@ def test_facade_and_circular_state(torch_cuda, golden):
     got = np.zeros(16, np.int32)
     _lib.check(_lib.load().b200dvb_codec_circular_lut(c._codec.handle.h, _lib.host_ptr(got)))
     assert np.array_equal(got, lut)
+
+
+@pytest.mark.parametrize("N", [48, 212])
+def test_siso_edge_values(torch_cuda, N):
+    """Ties, zeros, signed zeros, saturating and clipping inputs: still bit-exact."""
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    o = oracle.OracleTurbo(N, '1/3', 1)
+    rs = np.random.RandomState(N)
+    cases = []
+    z32 = np.zeros(N, np.float32); z64 = np.zeros(N)
+    cases.append(([z32] * 4, [z64] * 2, 0.7))                                   # all ties
+    cases.append(([np.full(N, -0.0, np.float32)] * 4, [np.full(N, -0.0)] * 2, 1.0))
+    big = [(rs.choice([-50.0, 50.0], N)).astype(np.float32) for _ in range(4)]
+    cases.append((big, [rs.choice([-300.0, 300.0], N) for _ in range(2)], 0.7))  # saturated, clips at +-300
+    huge = [(rs.randn(N) * 1e4).astype(np.float32) for _ in range(4)]
+    cases.append((huge, [rs.randn(N) * 1e4 for _ in range(2)], 1.0))
+    tiny = [(rs.randn(N) * 1e-30).astype(np.float32) for _ in range(4)]
+    cases.append((tiny, [rs.randn(N) * 1e-200 for _ in range(2)], 0.7))
+    quant = [(rs.randint(-4, 5, N) * 0.5).astype(np.float32) for _ in range(4)]   # many exact ties
+    cases.append((quant, [rs.randint(-4, 5, N) * 0.25 for _ in range(2)], 0.7))
+    punct = [quant[0], quant[1], z32, quant[3]]                                  # a punctured parity stream
+    cases.append((punct, [z64, z64], 0.7))
+    args = (o.next_state, o.out_W, o.out_Y, o.prev_state, o.prev_input, N)
+    for i, (Lc, La, sf) in enumerate(cases):
+        ga, gb = turbo.bcjr_max_log_map(*Lc, *La, *args, sf)
+        ra, rb = o.siso(*Lc, *La, sf)
+        assert np.array_equal(ga, ra) and np.array_equal(gb, rb), f"case {i}"
+
+
+def test_decode_all_zero_and_saturated_frames(torch_cuda):
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    for N, rate in ((48, '1/2'), (212, '1/3')):
+        g = turbo.DVBRCS2_Turbo(N, rate, 8)
+        o = oracle.OracleTurbo(N, rate, 8, perm=g.perm, inv_perm=g.inv_perm)
+        rs = np.random.RandomState(9)
+        llr = np.stack([np.zeros(g.n_llr, np.float32),
+                        rs.choice([-50.0, 50.0], g.n_llr).astype(np.float32),
+                        (rs.randint(-3, 4, g.n_llr) * 1.0).astype(np.float32),
+                        np.full(g.n_llr, 50.0, np.float32)])
+        assert np.array_equal(g.decode_batch(llr), o.decode_batch(llr))

@@ -53,3 +53,17 @@ def test_sweep_independent_of_batching(mod):
         for key in ("bit_errors", "frame_errors", "frames", "bits"):
             assert p[key] == x[key] + y[key]
     assert a["points"][0]["frames"] == 4096 and a["points"][0]["bits"] == 4096 * 96
+
+
+def test_tmem_selftest_and_microbench():
+    """tcgen05 alloc/st/ld/dealloc round trip (the decoder parks checkpoints in TMEM) and
+    the issue-rate probes bench.py quotes."""
+    import ctypes
+    from modulations_b200 import _lib
+    lib = _lib.load()
+    e = ctypes.c_int(-1)
+    _lib.check(lib.b200dvb_tmem_selftest(ctypes.byref(e)), "tmem_selftest")
+    assert e.value == 0
+    r = np.zeros(8)
+    _lib.check(lib.b200dvb_microbench(_lib.host_ptr(r)), "microbench")
+    assert 100 < r[0] < 140 and 100 < r[1] < 140 and 28 < r[3] < 36      # FADD, FMNMX, SHFL lane-ops/clk/SM

@@ -816,7 +816,8 @@ int quad_configure(Codec &c)
         bool ok = false;
         for (; gr >= 1 && !ok; --gr) {
             t.groups = gr;
-            for (t.frames = 8 * gr; t.frames > 8 * (gr - 1) && t.frames >= 1; --t.frames) {
+            const int fcap = getenv("B200DVB_FRAMES") ? atoi(getenv("B200DVB_FRAMES")) : 8 * gr;
+            for (t.frames = fcap < 8 * gr ? fcap : 8 * gr; t.frames > 8 * (gr - 1) && t.frames >= 1; --t.frames) {
                 t.smem_bytes = quad_smem_bytes(t);
                 if (t.smem_bytes <= cap) { ok = true; break; }
             }

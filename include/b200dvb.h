@@ -160,6 +160,10 @@ int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
  * over CTAs (synchronises the device).  out8_h: double[8] = {prep, recursion-in,
  * recursion-out + extrinsic, epilogue, hard decision, CTA total, 0, 0}. */
 int b200dvb_debug_phase_cycles(double *out8_h, int reset);
+/* Same for the thread-per-frame kernel (summed over warps): {transpose-in, pass 1 first half
+ * incl. prep, pass 1 second half, pass 2 to the crossing, out-phase windows in shared memory,
+ * out-phase windows in tensor memory, hard decision, warp total}. */
+int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the
  * two warps of a lane quadrant, as the decoder uses it; *errors_h = mismatching words. */

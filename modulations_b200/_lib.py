@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200dvb_demap": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_float, _c_float, _c_void_p, _c_void_p]),
     "b200dvb_hard_demod": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "b200dvb_debug_phase_cycles": (_c_int, [_c_void_p, _c_int]),
+    "b200dvb_debug_tpf_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_tmem_selftest": (_c_int, [_c_void_p]),
     "b200dvb_microbench": (_c_int, [_c_void_p]),
 }

@@ -153,6 +153,8 @@ int b200dvb_codec_create(int N, const int32_t *next_state_h, const int32_t *out_
     circular_lut(next_state_h, N, c.circ_lut);
     int rc = quad_configure(c);
     if (rc != B200DVB_OK) { delete h; return rc; }
+    rc = tpf_configure(c);
+    if (rc != B200DVB_OK) { delete h; return rc; }
     // stream offsets (depuncture order of dvb_rcs2_turbo.py:476-487)
     c.h_tab = (int16_t *)malloc(sizeof(int16_t) * 7 * N);
     if (!c.h_tab) { delete h; return B200DVB_ENOMEM; }
@@ -224,7 +226,8 @@ int b200dvb_siso(b200dvb_codec_t codec, int B, const float *Lc_A, const float *L
 
 size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B)
 {
-    return (codec && B > 0) ? decode_workspace_bytes(codec->c, B) : 0;
+    if (!codec || B <= 0) return 0;
+    return codec->c.tpf.enabled ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
 }
 
 int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr_stride,
@@ -234,6 +237,9 @@ int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr
 {
     if (!codec || B < 0 || !llr || (B && !workspace)) return B200DVB_EINVAL;
     if (llr_stride < codec->c.n_llr) return B200DVB_EINVAL;
+    if (codec->c.tpf.enabled)
+        return tpf_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters, workspace,
                          workspace_bytes, (cudaStream_t)stream);
 }
@@ -345,6 +351,12 @@ int b200dvb_debug_phase_cycles(double *out8_h, int reset)
 {
     if (!out8_h) return B200DVB_EINVAL;
     return read_phase_cycles(out8_h, reset);
+}
+
+int b200dvb_debug_tpf_cycles(double *out8_h, int reset)
+{
+    if (!out8_h) return B200DVB_EINVAL;
+    return tpf_read_phase_cycles(out8_h, reset);
 }
 
 int b200dvb_tmem_selftest(int *errors_h)

@@ -45,10 +45,29 @@ struct QuadGeom {
     size_t smem_bytes;
 };
 
+// ---- thread-per-frame decoder geometry (decode_tpf.cu) ----------------------
+constexpr int kTpfFrames = 16;      // frames per warp: lanes 0-15 run alpha, lanes 16-31 beta of the same frames
+constexpr int kTpfWarps = 4;        // one warp per SM sub-partition, each with its own TMEM lane quadrant
+constexpr int kTpfWin = 4;          // checkpoint spacing / recompute window (steps)
+
+struct TpfGeom {
+    int enabled;      // this codec is decoded by the thread-per-frame kernel
+    int N, M;         // couples per frame; crossing point M = N / 2
+    int T;            // branch-metric records per frame end kept in tensor memory ([0,T) and [N-T,N))
+    int mid;          // records per frame kept in shared memory ([T, N-T))
+    int nfull, rag;   // full recompute windows per half and length of the ragged last one (M % kTpfWin)
+    int nslots;       // checkpoints per lane
+    int tmem_cols;    // TMEM columns allocated per CTA (power of two >= 8 T, >= 32)
+    size_t smem_bytes;
+    size_t off_l1, off_l2, off_le, off_lef, off_y, off_ck;   // byte offsets in a warp's workspace
+    size_t ws_per_warp;
+};
+
 struct Codec {
     int N = 0, period = 0, iterations = 0, n_llr = 0;
     double sf_inner = 0.7, sf_last = 1.0;
     QuadGeom geom{};
+    TpfGeom tpf{};
     int num_sms = 0;
     int vec_ab = 0, vec_wy = 0;   // (A,B) / (W,Y) LLR pairs are adjacent and even-aligned in the stream
     // device tables
@@ -82,6 +101,12 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
 size_t decode_workspace_bytes(const Codec &c, int B);
 size_t siso_workspace_bytes(const Codec &c, int B);
 int quad_configure(Codec &c);
+int tpf_configure(Codec &c);
+int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
+                      uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,
+                      void *ws, size_t ws_bytes, cudaStream_t s);
+size_t tpf_workspace_bytes(const Codec &c, int B);
+int tpf_read_phase_cycles(double *out_h, int reset);
 int read_phase_cycles(double *out_h, int reset);
 
 int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,

@@ -1,0 +1,697 @@
+// decode_tpf.cu — thread-per-frame ("TPF") max-log-MAP turbo decoder, bit-exact with the
+// reference (dvb_rcs2_turbo.py:116-281 bcjr_max_log_map, :464-537 decode).
+//
+// Why: a thread that holds all 16 state metrics of one frame and one
+// direction needs no shuffle and no shared-memory exchange — a trellis step is 32 FADD +
+// 16 FMNMX + 16 FSUB of straight-line code with 16-way instruction-level parallelism, so ONE
+// warp per SM sub-partition saturates the FP32 pipe (measured: 61.7 cycles per step).  What
+// kept this mapping out of reach was storage: 32 B of branch metrics per step per frame,
+// 64 frames per SM to feed four warps = 434 KB.  Here the SM's two on-chip memories are
+// pooled: tensor memory (256 KB, otherwise idle — the decoder has no MMA) holds the records
+// of the outer T steps of either frame end, shared memory the middle ones.
+//
+// Mapping:
+//   * CTA = 4 warps, one per sub-partition / TMEM lane quadrant; a warp owns 16 frames for
+//     the whole decode and never synchronises with the other warps.
+//   * lane f (< 16) = forward (alpha) thread of frame f, lane 16 + f = backward (beta) thread
+//     of the same frame.  During the two "in" passes the beta lanes work in bit-reversed
+//     state labels, which gives their recursion the alpha wiring (tpf_core.cuh): one
+//     instruction stream serves both half-warps.
+//   * records [0, T) of frame f live in TMEM lane f (column 8k), records [N-T, N) in TMEM lane
+//     16 + f in REVERSED order (column 8(N-1-k)): while alpha walks up and beta walks down,
+//     both read "their" record with one tcgen05.ld.32x32b at the same column.  Where the
+//     accesses cross (end of pass 1) tcgen05.ld.16x32bx2 lets thread f and thread 16 + f read
+//     the same TMEM lane.
+//   * prep (gather, a-priori add, float64 branch sums) is fused into the first half of pass
+//     1: the alpha lane builds records 0.., the beta lane N-1.. exactly when it needs them.
+//   * meet in the middle (M = N/2) with a checkpoint every 8 steps; after the crossing the
+//     half-warps swap chains through a shuffle: the alpha lane walks beta down over [0, M),
+//     the beta lane walks alpha up over [M, N), each re-computing the other direction 8
+//     steps at a time from its OWN checkpoints (same operations, same order: exact).  The
+//     extrinsic epilogue (float64) is fused into that walk; a-priori / extrinsic values live
+//     in an L2-resident workspace laid out [step][frame] so every access is coalesced.
+#include "common.cuh"
+#include "tpf_core.cuh"
+
+#include <stdlib.h>
+
+namespace b200dvb {
+
+namespace {
+
+using namespace tpf;
+
+constexpr int kW = kTpfWin;
+
+// phase timers (SM cycles summed over warps): 0 transpose-in, 1 pass 1 first half (+prep), 2 pass 1
+// second half, 3 pass 2 to the crossing, 4 out-phase windows in shared memory, 5 out-phase windows
+// in tensor memory, 6 hard decision, 7 warp total
+__device__ unsigned long long g_tpf_cycles[8];
+
+struct TpfArgs {
+    TpfGeom g;
+    int B, iterations, n_tiles;
+    double sf_inner, sf_last;
+    const int16_t *tab;
+    const float *llr;
+    long long llr_stride;
+    int32_t *bits;
+    uint32_t *packed;
+    const uint8_t *ref_bits;
+    unsigned long long *counters;
+    unsigned char *ws;
+};
+
+// ---- tensor-memory access (lane-private scratchpad; no MMA anywhere in this kernel) ----
+__device__ __forceinline__ void tm_ld8(unsigned taddr, float (&g)[8])
+{   // thread t <- TMEM lane (quadrant + t), columns taddr.col .. +7
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]), "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_ld8_half(unsigned taddr, float (&g)[8])
+{   // threads t and t + 16 <- TMEM lane (taddr.lane + t), same columns (t < 16)
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], 0;"
+                 : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]), "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld(float (&g)[8])
+{   // the loaded registers become valid here: make every later use depend on this statement
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(g[0]), "+f"(g[1]), "+f"(g[2]), "+f"(g[3]), "+f"(g[4]), "+f"(g[5]), "+f"(g[6]), "+f"(g[7])
+                 :: "memory");
+}
+__device__ __forceinline__ void tm_st8(unsigned taddr, const float (&g)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3]), "f"(g[4]), "f"(g[5]), "f"(g[6]), "f"(g[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- cp.async (LDGSTS) into this warp's staging area: latency of the L2-resident workspace
+//      is hidden by depth, not by registers or by other warps (there are none) --------------
+__device__ __forceinline__ unsigned s_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cpa16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa16_stream(void *dst, const void *src, unsigned long long pol)
+{   // read-once data (channel LLRs): do not let it push the extrinsics out of L2
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+                 ::"r"(s_addr(dst)), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRing = 6;             // pass-1 prefetch ring depth (steps)
+// per-warp staging area: [0, 8K) beta vectors of the current window, [kW][4][32] float4 (the
+// pass-1 prefetch ring, 6 KB, aliases it); [8K, 10K) Z slot; [10K, 12K) X slot
+constexpr int kStageBytes = 12288;
+
+struct Ctx {
+    int N, M, T;
+    int f, isb, lane;                // frame within the tile, 0 = alpha lane / 1 = beta lane
+    unsigned tq;                     // TMEM address of this warp's lane quadrant, column 0
+    unsigned ycol;                   // first of the 4 kW spare TMEM columns that park the window's Y
+    float4 *srec;                    // this warp's shared-memory records: [(k - T) * 2 + half][16 frames]
+    unsigned char *stage;            // this warp's staging area (kStageBytes)
+    const int16_t *perm, *inv;       // shared-memory copies of the interleaver tables
+    float4 *L1A, *L2A;               // de-punctured channel LLRs [k][16]: (A,B,W1,Y1)[k] and (A,B)[perm k],(W2,Y2)[k]
+    double2 *Le, *LeF, *Yb;          // extrinsics (in place; last half-iteration -> LeF) and Y = Lc + La, [k][16]
+    float4 *CK;                      // checkpoints [slot][4][32 lanes]
+    unsigned long long pol;          // L2 evict-first policy for the channel LLRs
+    __device__ __forceinline__ float4 *wstore() const { return reinterpret_cast<float4 *>(stage); }
+    __device__ __forceinline__ float4 *slotZ() const { return reinterpret_cast<float4 *>(stage + 8192); }
+    __device__ __forceinline__ float4 *slotX() const { return reinterpret_cast<float4 *>(stage + 10240); }
+};
+
+__device__ __forceinline__ void smem_get(const Ctx &c, int k, float (&g)[8])
+{
+    const float4 lo = c.srec[((k - c.T) * 2) * 16 + c.f], hi = c.srec[((k - c.T) * 2 + 1) * 16 + c.f];
+    g[0] = lo.x; g[1] = lo.y; g[2] = lo.z; g[3] = lo.w; g[4] = hi.x; g[5] = hi.y; g[6] = hi.z; g[7] = hi.w;
+}
+__device__ __forceinline__ void smem_put(const Ctx &c, int k, const float (&g)[8])
+{
+    c.srec[((k - c.T) * 2) * 16 + c.f] = make_float4(g[0], g[1], g[2], g[3]);
+    c.srec[((k - c.T) * 2 + 1) * 16 + c.f] = make_float4(g[4], g[5], g[6], g[7]);
+}
+
+// ---- record fetch during the "in" passes, split into issue / complete so that the load of
+//      step j+1 is in flight while step j computes.  The alpha lane is at k = j, the beta lane
+//      at k = N-1-j.  KIND 0: TMEM, same column for both half-warps; 1: shared memory;
+//      2: TMEM crossed (alpha wants the partner's lane 16+f, beta lane f; same column). ----------
+struct Buf { float a[8], b[8]; };
+template <int KIND> __device__ __forceinline__ void pf_issue(const Ctx &c, int j, Buf &B)
+{
+    if (KIND == 0) tm_ld8(c.tq + 8u * j, B.a);
+    if (KIND == 1) smem_get(c, c.isb ? c.N - 1 - j : j, B.a);
+    if (KIND == 2) {
+        const unsigned col = 8u * (c.N - 1 - j);
+        tm_ld8_half(c.tq + col, B.b);                  // every thread <- lanes 0..15  (what the beta lanes want)
+        tm_ld8_half(c.tq + (16u << 16) + col, B.a);    // every thread <- lanes 16..31 (what the alpha lanes want)
+    }
+}
+template <int KIND> __device__ __forceinline__ void pf_complete(const Ctx &c, Buf &B, float (&g)[8])
+{
+    if (KIND == 0) tm_wait_ld(B.a);
+    if (KIND == 2) { tm_wait_ld(B.a); tm_wait_ld(B.b); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = (KIND == 2 && c.isb) ? B.b[i] : B.a[i];
+}
+
+__device__ __forceinline__ void ck_store(const Ctx &c, int slot, const float (&v)[16])
+{   // always in natural state order: the beta lanes hold rho4 labels during the passes
+    float n[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) n[s] = c.isb ? v[rho4(s)] : v[s];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        __stcg(c.CK + (slot * 4 + q) * 32 + c.lane, make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]));
+}
+
+// steps [j0, j1) of an "in" pass (j1 - j0 even), records of storage class KIND; CKPT: store a
+// checkpoint wherever (M - j) is a multiple of kW (pass 2 only; those j are even)
+template <int KIND, bool CKPT>
+__device__ __forceinline__ void run_pass(const Ctx &c, int j0, int j1, float (&v)[16])
+{
+    if (j0 >= j1) return;
+    Buf B0, B1;
+    float g[8];
+    pf_issue<KIND>(c, j0, B0);
+    pf_complete<KIND>(c, B0, g);
+    for (int j = j0; j < j1; j += 2) {
+        pf_issue<KIND>(c, j + 1, B1);
+        if (CKPT) {
+            if (((c.M - j) % kW) == 0) ck_store(c, (c.M - j) / kW - 1, v);
+            else if (j == 0) ck_store(c, c.M / kW, v);
+        }
+        pass_step(v, g, c.isb);
+        pf_complete<KIND>(c, B1, g);
+        if (j + 2 < j1) pf_issue<KIND>(c, j + 2, B0);
+        pass_step(v, g, c.isb);
+        if (j + 2 < j1) pf_complete<KIND>(c, B0, g);
+    }
+}
+
+__device__ __forceinline__ void issue_ckpt(const Ctx &c, int slot)
+{   // alpha lanes need their alpha checkpoint as X, beta lanes their beta checkpoint as Z
+    float4 *dst = (c.isb ? c.slotZ() : c.slotX()) + c.lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cpa16(dst + q * 32, c.CK + (slot * 4 + q) * 32 + c.lane);
+}
+__device__ __forceinline__ void slot_get(const float4 *slot, int lane, float (&v)[16])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = slot[q * 32 + lane];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void slot_put(float4 *slot, int lane, const float (&v)[16])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) slot[q * 32 + lane] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// ---- Y = Lc + La of the current window, parked in this lane's spare TMEM columns ------------
+__device__ __forceinline__ void tm_ld4(unsigned taddr, float (&y)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld4(float (&y)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(y[0]), "+f"(y[1]), "+f"(y[2]), "+f"(y[3]) :: "memory");
+}
+struct YQ { double2 y[kW]; };
+__device__ __forceinline__ void yq_load(const Ctx &c, int w0, int len, YQ &q)
+{   // global loads issued a whole window ahead of their use
+#pragma unroll
+    for (int u = 0; u < kW; ++u) q.y[u] = __ldcg(c.Yb + (w0 + min(u, len - 1)) * 16 + c.f);
+}
+__device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q)
+{
+#pragma unroll
+    for (int u = 0; u < kW; ++u)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                     :: "r"(c.tq + c.ycol + 4u * u), "r"(__double2loint(q.y[u].x)), "r"(__double2hiint(q.y[u].x)),
+                        "r"(__double2loint(q.y[u].y)), "r"(__double2hiint(q.y[u].y)) : "memory");
+    tm_wait_st();
+}
+
+// One recompute window of the "out" phase (all lanes in natural labels):
+//   alpha lane: steps [w0, w0+len) of [0, M): Z = running beta, X = alpha from its checkpoint
+//   beta lane:  steps [w0, w0+len) of [M, N): Z = beta from its checkpoint, X = running alpha
+// Both vectors arrive through the lane's staging slots (running ones written by the previous
+// window, checkpoints by cp.async), so the two half-warps run identical code.  First beta is
+// walked down through the window and parked in shared memory, then alpha is walked up with
+// the extrinsic fused in; the float64 epilogue of step u runs one step late so that its
+// dependent chain interleaves with the float32 work of step u+1.  Both loops are ROLLED and
+// branch-free: with one warp per sub-partition nothing hides an instruction-cache miss or a
+// dependency stall except the instruction scheduler.
+// TM: the window's records are in TMEM — column block (wa + u) for the alpha lane, block
+// (wa + len-1-u) for the beta lane (the high records are stored in reverse).
+template <bool TM>
+__device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, double sf,
+                                       double2 *LeOut, int nslot, int nw0, int nlen)
+{
+    Buf B;
+    auto issue = [&](int u) {
+        if (TM) { tm_ld8(c.tq + 8u * (wa + u), B.a); tm_ld8(c.tq + 8u * (wa + len - 1 - u), B.b); }
+        else    smem_get(c, w0 + u, B.a);
+    };
+    auto complete = [&](float (&g)[8]) {
+        if (TM) { tm_wait_ld(B.a); tm_wait_ld(B.b); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = (TM && c.isb) ? B.b[i] : B.a[i];
+    };
+    YQ nq;
+    if (nlen) yq_load(c, nw0, nlen, nq);                            // next window's Y: a window of time to arrive
+    float g[8];
+    float4 *ws = c.wstore() + c.lane;
+    {
+        float Z[16];
+        issue(len - 1);
+        slot_get(c.slotZ(), c.lane, Z);
+        complete(g);
+        for (int u = len - 1; u >= 0; --u) {
+            slot_put(ws + u * 128, 0, Z);                           // beta[k+1]
+            issue(u > 0 ? u - 1 : 0);                               // u == 0: first record of the way up
+            bwd_step(Z, g);
+            complete(g);
+        }
+        if (!c.isb) slot_put(c.slotZ(), c.lane, Z);                 // running beta of the alpha lane
+    }
+    float X[16];
+    slot_get(c.slotX(), c.lane, X);
+    if (nslot >= 0) issue_ckpt(c, nslot);
+    cpa_commit();
+    float yr[4], yn[4], uvp[4], zs[16];
+    tm_ld4(c.tq + c.ycol, yr);
+    issue(len > 1 ? 1 : 0);
+    slot_get(ws, 0, zs);
+    tm_wait_ld4(yr);
+    ext_step(X, zs, g, uvp);                                        // step 0
+    complete(g);
+    for (int u = 1; u < len; ++u) {
+        tm_ld4(c.tq + c.ycol + 4u * u, yn);
+        issue(u + 1 < len ? u + 1 : u);
+        slot_get(ws + u * 128, 0, zs);
+        float uv[4];
+        ext_step(X, zs, g, uv);
+        double ea, eb;                                              // epilogue of step u-1
+        make_extrinsic(uvp, __hiloint2double(__float_as_int(yr[1]), __float_as_int(yr[0])),
+                       __hiloint2double(__float_as_int(yr[3]), __float_as_int(yr[2])), sf, ea, eb);
+        __stcg(LeOut + (w0 + u - 1) * 16 + c.f, make_double2(ea, eb));
+        tm_wait_ld4(yn);
+        complete(g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { uvp[i] = uv[i]; yr[i] = yn[i]; }
+    }
+    {
+        double ea, eb;
+        make_extrinsic(uvp, __hiloint2double(__float_as_int(yr[1]), __float_as_int(yr[0])),
+                       __hiloint2double(__float_as_int(yr[3]), __float_as_int(yr[2])), sf, ea, eb);
+        __stcg(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
+    }
+    if (c.isb) slot_put(c.slotX(), c.lane, X);                      // running alpha of the beta lane
+    if (nlen) yq_park(c, nq);
+}
+
+// pass 1, first half, steps [j0, j1): build this thread's records on the fly (prep fused).  The
+// float64 chain of step j+1 and the float32 recursion of step j share one basic block.
+// TMST: records go to TMEM (j < T) / shared memory.  g, Y: record and Lc+La of step j0 on entry.
+template <bool FIRST, bool TMST>
+__device__ __forceinline__ void pass1a_range(const Ctx &c, int j0, int j1, const float4 *Lsrc,
+                                             const int16_t *tbl, int &slot, float (&g)[8], double2 &Y,
+                                             float (&v)[16])
+{
+    const int N = c.N, M = c.M;
+    unsigned char *ring = c.stage + c.lane * 32;
+    for (int jj = j0; jj < j1; ++jj) {
+        const int k = c.isb ? N - 1 - jj : jj;
+        // inputs of step jj+1 (clamped at the end: harmless re-computation of the last record)
+        cpa_wait<kRing - 1>();
+        const float4 x = *reinterpret_cast<const float4 *>(ring + slot * 1024);
+        double2 la = make_double2(0.0, 0.0);
+        if (!FIRST) la = *reinterpret_cast<const double2 *>(ring + slot * 1024 + 16);
+        {
+            const int jn = min(jj + 1 + kRing, M - 1);
+            const int kn = c.isb ? N - 1 - jn : jn;
+            cpa16_stream(ring + slot * 1024, Lsrc + kn * 16 + c.f, c.pol);
+            if (!FIRST) cpa16(ring + slot * 1024 + 16, c.Le + tbl[kn] * 16 + c.f);
+            cpa_commit();
+        }
+        slot = slot + 1 == kRing ? 0 : slot + 1;
+        const double YA = d_add((double)x.x, la.x);                 // Lc + La (:135)
+        const double YB = d_add((double)x.y, la.y);
+        float gn[8];
+        make_record(YA, YB, x.z, x.w, gn);
+        // step jj
+        if (TMST) tm_st8(c.tq + 8u * jj, g);
+        else      smem_put(c, k, g);
+        __stcg(c.Yb + k * 16 + c.f, Y);
+        pass_step(v, g, c.isb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = gn[i];
+        Y = make_double2(YA, YB);
+    }
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void pass1a(const Ctx &c, bool second, float (&v)[16])
+{
+    const int N = c.N, M = c.M;
+    const float4 *Lsrc = second ? c.L2A : c.L1A;
+    const int16_t *tbl = second ? c.perm : c.inv;                   // La = Le[perm k] (:507-508) / Le[inv k] (:523-524)
+    unsigned char *ring = c.stage + c.lane * 32;
+    for (int jj = 0; jj < kRing; ++jj) {
+        const int jn = min(jj, M - 1);
+        const int kn = c.isb ? N - 1 - jn : jn;
+        cpa16_stream(ring + jj * 1024, Lsrc + kn * 16 + c.f, c.pol);
+        if (!FIRST) cpa16(ring + jj * 1024 + 16, c.Le + tbl[kn] * 16 + c.f);
+        cpa_commit();
+    }
+    float g[8];
+    double2 Y;
+    int slot = 1 % kRing;
+    {   // step 0
+        cpa_wait<kRing - 1>();
+        const float4 x = *reinterpret_cast<const float4 *>(ring);
+        double2 la = make_double2(0.0, 0.0);
+        if (!FIRST) la = *reinterpret_cast<const double2 *>(ring + 16);
+        const int jn = min(kRing, M - 1);
+        const int kn = c.isb ? N - 1 - jn : jn;
+        cpa16_stream(ring, Lsrc + kn * 16 + c.f, c.pol);
+        if (!FIRST) cpa16(ring + 16, c.Le + tbl[kn] * 16 + c.f);
+        cpa_commit();
+        Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));
+        make_record(Y.x, Y.y, x.z, x.w, g);
+    }
+    pass1a_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, slot, g, Y, v);
+    pass1a_range<FIRST, false>(c, c.T, M, Lsrc, tbl, slot, g, Y, v);
+    cpa_wait<0>();
+}
+
+// One SISO half-iteration for the 16 frames of this warp.
+__device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool last, double sf, long long (&ph)[8])
+{
+    long long tA = clock64();
+    const int N = c.N, M = c.M, T = c.T, lane = c.lane;
+    double2 *LeOut = last ? c.LeF : c.Le;
+    float v[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) v[s] = 0.f;
+    // ---- pass 1, first half ------------------------------------------------------------------
+    if (first) pass1a<true>(c, second, v);
+    else       pass1a<false>(c, second, v);
+    tm_wait_st();
+    __syncwarp();
+    { const long long t = clock64(); ph[1] += t - tA; tA = t; }
+    // ---- pass 1, second half: the records the partner lane built ---------------------------
+    run_pass<1, false>(c, M, N - T, v);
+    run_pass<2, false>(c, N - T, N, v);
+    { const long long t = clock64(); ph[2] += t - tA; tA = t; }
+    // ---- pass 2 up to the crossing point, checkpoint every kW steps -------------------------
+    const int nfull = M / kW, rag = M % kW, nwin = nfull + (rag ? 1 : 0);
+    auto win_w0 = [&](int i) { return i < nfull ? (c.isb ? M + i * kW : M - (i + 1) * kW) : (c.isb ? N - rag : 0); };
+    auto win_len = [&](int i) { return i < nfull ? kW : rag; };
+    {
+        YQ q0;
+        yq_load(c, win_w0(0), win_len(0), q0);                      // Y of the first window: arrives during pass 2
+        run_pass<0, true>(c, 0, T, v);
+        run_pass<1, true>(c, T, M, v);
+        yq_park(c, q0);
+    }
+    { const long long t = clock64(); ph[3] += t - tA; tA = t; }
+    // ---- crossing: the half-warps swap chains (beta lanes back to natural labels): every lane
+    //      drops its vector into the PARTNER's slot -------------------------------------------
+    {
+        float n[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) n[s] = c.isb ? v[rho4(s)] : v[s];
+        slot_put(c.isb ? c.slotZ() : c.slotX(), lane ^ 16, n);
+    }
+    const int n_inner = (M - T) / kW;            // windows whose records are in shared memory
+    issue_ckpt(c, 0);
+    cpa_commit();
+    // ---- out phase: windows from the crossing point outwards ---------------------------------
+    for (int i = 0; i < nwin; ++i) {
+        cpa_wait<0>();
+        __syncwarp();
+        const int wa = i < nfull ? M - (i + 1) * kW : 0;
+        const int nlen = i + 1 < nwin ? win_len(i + 1) : 0;
+        const int nw0 = i + 1 < nwin ? win_w0(i + 1) : 0;
+        if (i < n_inner) window<false>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen);
+        else             window<true>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen);
+        if (i == n_inner - 1) { const long long t = clock64(); ph[4] += t - tA; tA = t; }
+    }
+    cpa_wait<0>();
+    __syncwarp();
+    { const long long t = clock64(); ph[5] += t - tA; tA = t; }
+}
+
+__global__ void __launch_bounds__(kTpfWarps * 32, 1)
+tpf_kernel(const TpfArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TpfGeom g = A.g;
+    const int N = g.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
+    const int tab_bytes = ((2 * N * 2 + 15) / 16) * 16;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_raw + tab_bytes);
+    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 16);
+    unsigned char *stage_all = reinterpret_cast<unsigned char *>(srec_all + (size_t)kTpfWarps * g.mid * 2 * 16);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * N; i += blockDim.x) tab[i] = A.tab[i];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    Ctx c;
+    c.N = N; c.M = g.M; c.T = g.T;
+    c.f = lane & 15; c.isb = lane >> 4; c.lane = lane;
+    c.tq = tmem_base + (((unsigned)warp * 32u) << 16);
+    c.ycol = 8u * g.T;
+    c.srec = srec_all + (size_t)warp * g.mid * 2 * 16;
+    c.stage = stage_all + (size_t)warp * kStageBytes;
+    c.perm = tab; c.inv = tab + N;
+    const int wg = blockIdx.x * kTpfWarps + warp;
+    unsigned char *ws = A.ws + (size_t)wg * g.ws_per_warp;
+    c.L1A = reinterpret_cast<float4 *>(ws + g.off_l1);
+    c.L2A = reinterpret_cast<float4 *>(ws + g.off_l2);
+    c.Le = reinterpret_cast<double2 *>(ws + g.off_le);
+    c.LeF = reinterpret_cast<double2 *>(ws + g.off_lef);
+    c.Yb = reinterpret_cast<double2 *>(ws + g.off_y);
+    c.CK = reinterpret_cast<float4 *>(ws + g.off_ck);
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.pol));
+    const int16_t *g_off = A.tab + 2 * N;        // offA, offW1, offY1, offW2, offY2 (global, read-only)
+
+    unsigned long long bit_err = 0, frm_err = 0, frames_done = 0;
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    for (int tile = wg; tile < A.n_tiles; tile += gridDim.x * kTpfWarps) {
+        const long long frame0 = (long long)tile * kTpfFrames;
+        const long long t0 = clock64();
+        // ---- de-puncture + transpose the 16 frames' LLRs into [k][frame] (:466-487, :507-512);
+        //      lane <-> k, 8 frames' loads in flight at a time ---------------------------------
+        for (int k = lane; k < N; k += 32) {
+            const int oa = __ldg(g_off + k), op = __ldg(g_off + c.perm[k]);
+            const int o0 = __ldg(g_off + N + k), o1 = __ldg(g_off + 2 * N + k);
+            const int o2 = __ldg(g_off + 3 * N + k), o3 = __ldg(g_off + 4 * N + k);
+#pragma unroll
+            for (int f0 = 0; f0 < kTpfFrames; f0 += 8) {
+                float4 x1[8], x2[8];
+#pragma unroll
+                for (int fr = 0; fr < 8; ++fr) {
+                    const long long frame = frame0 + f0 + fr;
+                    const float *Lf = A.llr + frame * A.llr_stride;
+                    x1[fr] = make_float4(0.f, 0.f, 0.f, 0.f); x2[fr] = x1[fr];
+                    if (frame < A.B) {
+                        x1[fr].x = __ldg(Lf + oa); x1[fr].y = __ldg(Lf + oa + 1);
+                        x2[fr].x = __ldg(Lf + op); x2[fr].y = __ldg(Lf + op + 1);
+                        if (o0 >= 0) x1[fr].z = __ldg(Lf + o0);
+                        if (o1 >= 0) x1[fr].w = __ldg(Lf + o1);
+                        if (o2 >= 0) x2[fr].z = __ldg(Lf + o2);
+                        if (o3 >= 0) x2[fr].w = __ldg(Lf + o3);
+                    }
+                }
+#pragma unroll
+                for (int fr = 0; fr < 8; ++fr) {
+                    __stcg(c.L1A + k * 16 + f0 + fr, x1[fr]);
+                    __stcg(c.L2A + k * 16 + f0 + fr, x2[fr]);
+                }
+            }
+        }
+        __syncwarp();
+        ph[0] += clock64() - t0;
+        for (int h = 0; h < 2 * A.iterations; ++h) {
+            const double sf = (h >> 1) < A.iterations - 1 ? A.sf_inner : A.sf_last;
+            siso(c, (h & 1) != 0, h == 0, h == 2 * A.iterations - 1, sf, ph);
+        }
+        const long long t6 = clock64();
+        // ---- hard decision (dvb_rcs2_turbo.py:526-537) + optional error counting ------------
+        const long long frame = frame0 + c.f;
+        const bool live = frame < A.B;
+        const int wpf = (2 * N + 31) / 32;
+        int any_err = 0;
+        for (int w = c.isb; w * 16 < N; w += 2) {
+            unsigned word = 0;
+#pragma unroll
+            for (int t0 = 0; t0 < 16; t0 += 8) {
+                float4 ab[8]; double2 la[8], e1[8]; uchar2 rb[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {                       // all loads of 8 couples in flight
+                    const int k = min(w * 16 + t0 + t, N - 1);
+                    ab[t] = __ldcg(c.L1A + k * 16 + c.f);
+                    la[t] = __ldcg(c.LeF + c.inv[k] * 16 + c.f);
+                    e1[t] = __ldcg(c.Le + k * 16 + c.f);
+                    rb[t] = make_uchar2(0, 0);
+                    if (live && A.ref_bits)
+                        rb[t] = *reinterpret_cast<const uchar2 *>(A.ref_bits + (size_t)frame * 2 * N + 2 * k);
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int k = w * 16 + t0 + t;
+                    if (k < N) {
+                        const double LA = d_add(d_add((double)ab[t].x, la[t].x), e1[t].x);
+                        const double LB = d_add(d_add((double)ab[t].y, la[t].y), e1[t].y);
+                        const int bA = LA < 0.0, bB = LB < 0.0;
+                        word |= (unsigned)(bA | (bB << 1)) << (2 * (t0 + t));
+                        if (live) {
+                            if (A.bits)
+                                *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * k) = make_int2(bA, bB);
+                            if (A.ref_bits) {
+                                const int errs = (bA != rb[t].x) + (bB != rb[t].y);
+                                bit_err += errs;
+                                any_err |= errs;
+                            }
+                        }
+                    }
+                }
+            }
+            if (live && A.packed) A.packed[(size_t)frame * wpf + w] = word;
+        }
+        any_err |= __shfl_xor_sync(0xffffffffu, any_err, 16);
+        if (live && !c.isb) { frames_done += 1; frm_err += any_err ? 1 : 0; }
+        __syncwarp();
+        ph[6] += clock64() - t6;
+    }
+    if (lane == 0) {
+        ph[7] = clock64() - t_begin;
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_tpf_cycles[i], (unsigned long long)ph[i]);
+    }
+    if (A.counters) {
+        for (int o = 16; o > 0; o >>= 1) {
+            bit_err += __shfl_xor_sync(0xffffffffu, bit_err, o);
+            frm_err += __shfl_xor_sync(0xffffffffu, frm_err, o);
+            frames_done += __shfl_xor_sync(0xffffffffu, frames_done, o);
+        }
+        if (lane == 0) {
+            if (bit_err) atomicAdd(A.counters + 0, bit_err);
+            if (frm_err) atomicAdd(A.counters + 1, frm_err);
+            if (frames_done) {
+                atomicAdd(A.counters + 2, frames_done);
+                atomicAdd(A.counters + 3, frames_done * 2ull * N);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+int tpf_configure(Codec &c)
+{
+    TpfGeom &g = c.tpf;
+    g = TpfGeom{};
+    const int N = c.N;
+    const char *e = getenv("B200DVB_KERNEL");
+    if (e && e[0] == 'q') return B200DVB_OK;                   // B200DVB_KERNEL=quad forces the older kernel
+    if (N < 16 || (N % 4) != 0) return B200DVB_OK;
+    const int M = N / 2;
+    int T = M < 64 ? M : 64;
+    while (T > 0 && (((M - T) % kW) != 0 || 8 * T + 4 * kW > 512)) --T;   // windows must not straddle TMEM / smem; Y columns
+    if (T < kW) return B200DVB_OK;
+    g.N = N; g.M = M; g.T = T; g.mid = N - 2 * T;
+    g.nfull = M / kW; g.rag = M % kW; g.nslots = g.nfull + (g.rag ? 1 : 0);
+    g.tmem_cols = 32;
+    while (g.tmem_cols < 8 * T + 4 * kW) g.tmem_cols *= 2;        // records + the window's Y
+    if (g.tmem_cols > 512) return B200DVB_OK;
+    const size_t tab_bytes = ((size_t)2 * N * 2 + 15) / 16 * 16;
+    g.smem_bytes = tab_bytes + 16 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
+    int dev = 0;
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (g.smem_bytes > (size_t)prop.sharedMemPerBlockOptin) return B200DVB_OK;   // falls back to the quad kernel
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    g.off_l1 = take((size_t)N * 16 * sizeof(float4));
+    g.off_l2 = take((size_t)N * 16 * sizeof(float4));
+    g.off_le = take((size_t)N * 16 * sizeof(double2));
+    g.off_lef = take((size_t)N * 16 * sizeof(double2));
+    g.off_y = take((size_t)N * 16 * sizeof(double2));
+    g.off_ck = take((size_t)g.nslots * 4 * 32 * sizeof(float4));
+    g.ws_per_warp = off;
+    B2_CUDA(cudaFuncSetAttribute(tpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    g.enabled = 1;
+    return B200DVB_OK;
+}
+
+int tpf_read_phase_cycles(double *out_h, int reset)
+{
+    unsigned long long h[8];
+    B2_CUDA(cudaMemcpyFromSymbol(h, g_tpf_cycles, sizeof h));
+    for (int i = 0; i < 8; ++i) out_h[i] = (double)h[i];
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        B2_CUDA(cudaMemcpyToSymbol(g_tpf_cycles, z, sizeof z));
+    }
+    return B200DVB_OK;
+}
+
+static int tpf_grid(const Codec &c, int B)
+{
+    const int tiles = (B + kTpfFrames - 1) / kTpfFrames;
+    const int ctas = (tiles + kTpfWarps - 1) / kTpfWarps;
+    return ctas < c.num_sms ? ctas : c.num_sms;
+}
+
+size_t tpf_workspace_bytes(const Codec &c, int B)
+{
+    return (size_t)tpf_grid(c, B) * kTpfWarps * c.tpf.ws_per_warp + 256;
+}
+
+int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
+                      uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,
+                      void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    if (ws_bytes < tpf_workspace_bytes(c, B)) return B200DVB_ENOMEM;
+    TpfArgs A{};
+    A.g = c.tpf; A.B = B; A.iterations = c.iterations;
+    A.n_tiles = (B + kTpfFrames - 1) / kTpfFrames;
+    A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
+    A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
+    A.ref_bits = ref_bits; A.counters = counters;
+    A.ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    tpf_kernel<<<tpf_grid(c, B), kTpfWarps * 32, c.tpf.smem_bytes, s>>>(A);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+}  // namespace b200dvb

@@ -19,7 +19,7 @@ void orc_bcjr_max_log_map(const float *Lc_A, const float *Lc_B, const float *Lc_
 }
 
 using namespace b200dvb::tpf;
-constexpr int W = 8;
+constexpr int W = 4;
 
 static double urand() { return (double)rand() / RAND_MAX; }
 

@@ -50,7 +50,7 @@ __device__ unsigned long long g_tpf_cycles[8];
 
 struct TpfArgs {
     TpfGeom g;
-    int B, iterations, n_tiles;
+    int B, iterations, n_tiles, n_llr, vec, prefetch;
     double sf_inner, sf_last;
     const int16_t *tab;
     const float *llr;
@@ -319,78 +319,84 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
     if (nlen) yq_park(c, nq);
 }
 
-// pass 1, first half, steps [j0, j1): build this thread's records on the fly (prep fused).  The
-// float64 chain of step j+1 and the float32 recursion of step j share one basic block.
-// TMST: records go to TMEM (j < T) / shared memory.  g, Y: record and Lc+La of step j0 on entry.
+// pass 1, first half, steps [j0, j1) (even count): build this thread's records on the fly (prep
+// fused).  Two steps per iteration: the float64 chains of steps j+2 and j+3 and the float32
+// recursion of steps j and j+1 share one basic block, so the scheduler can interleave them.
+// TMST: records go to TMEM (j < T) / shared memory.  PrepState: records and Lc+La of steps j0, j0+1.
+struct PrepState { float gA[8], gB[8]; double2 YA, YB; int ps; };
+__device__ __forceinline__ void prep_load(const Ctx &c, unsigned char *dst, int jn, const float4 *Lsrc,
+                                          const int16_t *tbl, bool first)
+{   // loads for the prep of this thread's position of step jn (:507-512, :523-524)
+    jn = min(jn, c.M - 1);
+    const int kn = c.isb ? c.N - 1 - jn : jn;
+    cpa16_stream(dst, Lsrc + kn * 16 + c.f, c.pol);
+    if (!first) cpa16(dst + 16, c.Le + tbl[kn] * 16 + c.f);
+}
+template <bool FIRST>
+__device__ __forceinline__ void prep_record(const unsigned char *src, float (&g)[8], double2 &Y)
+{
+    const float4 x = *reinterpret_cast<const float4 *>(src);
+    double2 la = make_double2(0.0, 0.0);
+    if (!FIRST) la = *reinterpret_cast<const double2 *>(src + 16);
+    Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));    // Lc + La (:135)
+    make_record(Y.x, Y.y, x.z, x.w, g);
+}
 template <bool FIRST, bool TMST>
 __device__ __forceinline__ void pass1a_range(const Ctx &c, int j0, int j1, const float4 *Lsrc,
-                                             const int16_t *tbl, int &slot, float (&g)[8], double2 &Y,
-                                             float (&v)[16])
+                                             const int16_t *tbl, PrepState &P, float (&v)[16])
 {
-    const int N = c.N, M = c.M;
+    const int N = c.N;
     unsigned char *ring = c.stage + c.lane * 32;
-    for (int jj = j0; jj < j1; ++jj) {
-        const int k = c.isb ? N - 1 - jj : jj;
-        // inputs of step jj+1 (clamped at the end: harmless re-computation of the last record)
-        cpa_wait<kRing - 1>();
-        const float4 x = *reinterpret_cast<const float4 *>(ring + slot * 1024);
-        double2 la = make_double2(0.0, 0.0);
-        if (!FIRST) la = *reinterpret_cast<const double2 *>(ring + slot * 1024 + 16);
-        {
-            const int jn = min(jj + 1 + kRing, M - 1);
-            const int kn = c.isb ? N - 1 - jn : jn;
-            cpa16_stream(ring + slot * 1024, Lsrc + kn * 16 + c.f, c.pol);
-            if (!FIRST) cpa16(ring + slot * 1024 + 16, c.Le + tbl[kn] * 16 + c.f);
-            cpa_commit();
-        }
-        slot = slot + 1 == kRing ? 0 : slot + 1;
-        const double YA = d_add((double)x.x, la.x);                 // Lc + La (:135)
-        const double YB = d_add((double)x.y, la.y);
-        float gn[8];
-        make_record(YA, YB, x.z, x.w, gn);
-        // step jj
-        if (TMST) tm_st8(c.tq + 8u * jj, g);
-        else      smem_put(c, k, g);
-        __stcg(c.Yb + k * 16 + c.f, Y);
-        pass_step(v, g, c.isb);
+    for (int jj = j0; jj < j1; jj += 2) {
+        // records of steps jj+2, jj+3 (clamped at the end: harmless re-computation)
+        cpa_wait<2>();
+        unsigned char *slot = ring + P.ps * 2048;
+        float gC[8], gD[8];
+        double2 YC, YD;
+        prep_record<FIRST>(slot, gC, YC);
+        prep_record<FIRST>(slot + 1024, gD, YD);
+        prep_load(c, slot, jj + 8, Lsrc, tbl, FIRST);
+        prep_load(c, slot + 1024, jj + 9, Lsrc, tbl, FIRST);
+        cpa_commit();
+        P.ps = P.ps == 2 ? 0 : P.ps + 1;
+        // steps jj, jj+1
+        const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
+        if (TMST) tm_st8(c.tq + 8u * jj, P.gA);
+        else      smem_put(c, k0, P.gA);
+        __stcg(c.Yb + k0 * 16 + c.f, P.YA);
+        pass_step(v, P.gA, c.isb);
+        if (TMST) tm_st8(c.tq + 8u * (jj + 1), P.gB);
+        else      smem_put(c, k1, P.gB);
+        __stcg(c.Yb + k1 * 16 + c.f, P.YB);
+        pass_step(v, P.gB, c.isb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = gn[i];
-        Y = make_double2(YA, YB);
+        for (int i = 0; i < 8; ++i) { P.gA[i] = gC[i]; P.gB[i] = gD[i]; }
+        P.YA = YC; P.YB = YD;
     }
 }
 
 template <bool FIRST>
 __device__ __forceinline__ void pass1a(const Ctx &c, bool second, float (&v)[16])
 {
-    const int N = c.N, M = c.M;
     const float4 *Lsrc = second ? c.L2A : c.L1A;
     const int16_t *tbl = second ? c.perm : c.inv;                   // La = Le[perm k] (:507-508) / Le[inv k] (:523-524)
     unsigned char *ring = c.stage + c.lane * 32;
-    for (int jj = 0; jj < kRing; ++jj) {
-        const int jn = min(jj, M - 1);
-        const int kn = c.isb ? N - 1 - jn : jn;
-        cpa16_stream(ring + jj * 1024, Lsrc + kn * 16 + c.f, c.pol);
-        if (!FIRST) cpa16(ring + jj * 1024 + 16, c.Le + tbl[kn] * 16 + c.f);
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {                                   // ring of 3 step pairs
+        prep_load(c, ring + p * 2048, 2 * p, Lsrc, tbl, FIRST);
+        prep_load(c, ring + p * 2048 + 1024, 2 * p + 1, Lsrc, tbl, FIRST);
         cpa_commit();
     }
-    float g[8];
-    double2 Y;
-    int slot = 1 % kRing;
-    {   // step 0
-        cpa_wait<kRing - 1>();
-        const float4 x = *reinterpret_cast<const float4 *>(ring);
-        double2 la = make_double2(0.0, 0.0);
-        if (!FIRST) la = *reinterpret_cast<const double2 *>(ring + 16);
-        const int jn = min(kRing, M - 1);
-        const int kn = c.isb ? N - 1 - jn : jn;
-        cpa16_stream(ring, Lsrc + kn * 16 + c.f, c.pol);
-        if (!FIRST) cpa16(ring + 16, c.Le + tbl[kn] * 16 + c.f);
-        cpa_commit();
-        Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));
-        make_record(Y.x, Y.y, x.z, x.w, g);
-    }
-    pass1a_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, slot, g, Y, v);
-    pass1a_range<FIRST, false>(c, c.T, M, Lsrc, tbl, slot, g, Y, v);
+    PrepState P;
+    cpa_wait<2>();
+    prep_record<FIRST>(ring, P.gA, P.YA);                            // steps 0, 1
+    prep_record<FIRST>(ring + 1024, P.gB, P.YB);
+    prep_load(c, ring, 6, Lsrc, tbl, FIRST);
+    prep_load(c, ring + 1024, 7, Lsrc, tbl, FIRST);
+    cpa_commit();
+    P.ps = 1;
+    pass1a_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
+    pass1a_range<FIRST, false>(c, c.T, c.M, Lsrc, tbl, P, v);
     cpa_wait<0>();
 }
 
@@ -462,7 +468,7 @@ tpf_kernel(const TpfArgs A)
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((2 * N * 2 + 15) / 16) * 16;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_raw + tab_bytes);
-    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 16);
+    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 32);
     unsigned char *stage_all = reinterpret_cast<unsigned char *>(srec_all + (size_t)kTpfWarps * g.mid * 2 * 16);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -481,7 +487,14 @@ tpf_kernel(const TpfArgs A)
     c.tq = tmem_base + (((unsigned)warp * 32u) << 16);
     c.ycol = 8u * g.T;
     c.srec = srec_all + (size_t)warp * g.mid * 2 * 16;
-    c.stage = stage_all + (size_t)warp * kStageBytes;
+    {   // ptxas folds a warp-uniform base into a [R+UR+imm] shared-memory operand; for LDGSTS (cp.async)
+        // that form raises "illegal instruction" on sm_100a, so the staging base goes through memory
+        volatile unsigned *slots = reinterpret_cast<volatile unsigned *>(smem_raw + tab_bytes);
+        if (lane == 0) slots[4 + warp] = (unsigned)warp * kStageBytes;
+        __syncwarp();
+        c.stage = stage_all + slots[4 + warp];
+        __syncwarp();
+    }
     c.perm = tab; c.inv = tab + N;
     const int wg = blockIdx.x * kTpfWarps + warp;
     unsigned char *ws = A.ws + (size_t)wg * g.ws_per_warp;
@@ -527,6 +540,17 @@ tpf_kernel(const TpfArgs A)
                 for (int fr = 0; fr < 8; ++fr) {
                     __stcg(c.L1A + k * 16 + f0 + fr, x1[fr]);
                     __stcg(c.L2A + k * 16 + f0 + fr, x2[fr]);
+                }
+            }
+        }
+        if (A.prefetch) {   // pull the next tile's rows into L2 while this one decodes
+            const long long nf0 = frame0 + (long long)gridDim.x * kTpfWarps * kTpfFrames;
+            const int lines = (A.n_llr * 4 + 127) / 128;
+            for (int i = lane; i < kTpfFrames * lines; i += 32) {
+                const long long frame = nf0 + i / lines;
+                if (frame < A.B) {
+                    const float *pl = A.llr + frame * A.llr_stride + (i % lines) * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
                 }
             }
         }
@@ -632,7 +656,7 @@ int tpf_configure(Codec &c)
     while (g.tmem_cols < 8 * T + 4 * kW) g.tmem_cols *= 2;        // records + the window's Y
     if (g.tmem_cols > 512) return B200DVB_OK;
     const size_t tab_bytes = ((size_t)2 * N * 2 + 15) / 16 * 16;
-    g.smem_bytes = tab_bytes + 16 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
+    g.smem_bytes = tab_bytes + 32 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
     int dev = 0;
     cudaDeviceProp prop;
     B2_CUDA(cudaGetDevice(&dev));
@@ -685,6 +709,10 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     TpfArgs A{};
     A.g = c.tpf; A.B = B; A.iterations = c.iterations;
     A.n_tiles = (B + kTpfFrames - 1) / kTpfFrames;
+    A.n_llr = c.n_llr;
+    A.prefetch = getenv("B200DVB_PREFETCH") ? atoi(getenv("B200DVB_PREFETCH")) : 0;
+    A.vec = c.vec_ab && c.vec_wy && (llr_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 7) == 0);
+    if (getenv("B200DVB_NOVEC")) A.vec = 0;
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;

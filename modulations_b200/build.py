@@ -49,7 +49,23 @@ def build(force=False, verbose=False):
         print(log)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libb200dvb.so (see modulations_b200/build.log)")
+    _check_sass()
     return LIB
+
+
+def _check_sass():
+    """ptxas 12.9 may fold a warp-uniform base into the shared-memory operand of cp.async
+    (`LDGSTS [R+UR+imm]`); that form raises "illegal instruction" on sm_100a (found on the B200,
+    DESIGN.md §4.1).  The kernels route such bases through memory; make sure it stays that way."""
+    import re
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    except OSError:
+        return
+    bad = [l for l in sass.splitlines() if re.search(r"LDGSTS.*\[R\d+\+UR", l)]
+    if bad:
+        raise RuntimeError("libb200dvb.so contains LDGSTS with a [R+UR+imm] destination (faults on sm_100a):\n"
+                           + "\n".join(bad[:5]))
 
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ __device__ unsigned long long g_tpf_cycles[8];
 
 struct TpfArgs {
     TpfGeom g;
-    int B, iterations, n_tiles, n_llr, vec, prefetch;
+    int B, iterations, n_tiles, n_llr, vec4;
     double sf_inner, sf_last;
     const int16_t *tab;
     const float *llr;
@@ -92,22 +92,35 @@ __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sy
 // ---- cp.async (LDGSTS) into this warp's staging area: latency of the L2-resident workspace
 //      is hidden by depth, not by registers or by other warps (there are none) --------------
 __device__ __forceinline__ unsigned s_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cpa16(void *dst, const void *src)
+// `one` is the value 1 read back from shared memory (Ctx::one).  ptxas 12.9 folds any warp-uniform
+// part of the destination into a [R+UR+imm] operand, and LDGSTS with that operand form raises
+// "illegal instruction" on sm_100a (found on the B200; modulations_b200/build.py checks the
+// SASS).  A product with a value ptxas cannot see through keeps the address in one register.
+__device__ __forceinline__ void cpa16(void *dst, const void *src, unsigned one)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst) * one), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cpa16_stream(void *dst, const void *src, unsigned long long pol)
+__device__ __forceinline__ void cpa16_stream(void *dst, const void *src, unsigned long long pol, unsigned one)
 {   // read-once data (channel LLRs): do not let it push the extrinsics out of L2
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
-                 ::"r"(s_addr(dst)), "l"(src), "l"(pol) : "memory");
+                 ::"r"(s_addr(dst) * one), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kRing = 6;             // pass-1 prefetch ring depth (steps)
+// The workspace is scratch: once a line of Y / checkpoints / old extrinsics has been consumed it
+// is dead until it is rewritten.  discard.global.L2 drops it WITHOUT a write-back, so the 160 MB of
+// scratch of the resident warps stops streaming through HBM (it was 150 KB of DRAM writes per frame).
+__device__ __forceinline__ void l2_discard(const void *line128)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(line128) : "memory");
+}
+
+constexpr int kRingPairs = 4;        // pass-1 prefetch ring depth in step pairs (2 KB each: the whole beta-vector area)
 // per-warp staging area: [0, 8K) beta vectors of the current window, [kW][4][32] float4 (the
 // pass-1 prefetch ring, 6 KB, aliases it); [8K, 10K) Z slot; [10K, 12K) X slot
 constexpr int kStageBytes = 12288;
+constexpr int kRowFloats = kStageBytes / 8;   // transposition: two frame rows of up to 1536 LLRs each share the staging area
 
 struct Ctx {
     int N, M, T;
@@ -121,6 +134,7 @@ struct Ctx {
     double2 *Le, *LeF, *Yb;          // extrinsics (in place; last half-iteration -> LeF) and Y = Lc + La, [k][16]
     float4 *CK;                      // checkpoints [slot][4][32 lanes]
     unsigned long long pol;          // L2 evict-first policy for the channel LLRs
+    unsigned one;                    // 1, opaque to the compiler (see cpa16)
     __device__ __forceinline__ float4 *wstore() const { return reinterpret_cast<float4 *>(stage); }
     __device__ __forceinline__ float4 *slotZ() const { return reinterpret_cast<float4 *>(stage + 8192); }
     __device__ __forceinline__ float4 *slotX() const { return reinterpret_cast<float4 *>(stage + 10240); }
@@ -198,7 +212,7 @@ __device__ __forceinline__ void issue_ckpt(const Ctx &c, int slot)
 {   // alpha lanes need their alpha checkpoint as X, beta lanes their beta checkpoint as Z
     float4 *dst = (c.isb ? c.slotZ() : c.slotX()) + c.lane;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cpa16(dst + q * 32, c.CK + (slot * 4 + q) * 32 + c.lane);
+    for (int q = 0; q < 4; ++q) cpa16(dst + q * 32, c.CK + (slot * 4 + q) * 32 + c.lane, c.one);
 }
 __device__ __forceinline__ void slot_get(const float4 *slot, int lane, float (&v)[16])
 {
@@ -230,14 +244,20 @@ __device__ __forceinline__ void yq_load(const Ctx &c, int w0, int len, YQ &q)
 #pragma unroll
     for (int u = 0; u < kW; ++u) q.y[u] = __ldcg(c.Yb + (w0 + min(u, len - 1)) * 16 + c.f);
 }
-__device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q)
+__device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int len)
 {
+
 #pragma unroll
     for (int u = 0; u < kW; ++u)
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
                      :: "r"(c.tq + c.ycol + 4u * u), "r"(__double2loint(q.y[u].x)), "r"(__double2hiint(q.y[u].x)),
                         "r"(__double2loint(q.y[u].y)), "r"(__double2hiint(q.y[u].y)) : "memory");
     tm_wait_st();
+    // the values are in TMEM now.  The window's Y of both half-warps are 2 x len x 2 lines of 128 bytes:
+    // one predicated discard instruction, lane = (half-warp, step, half line)
+    const int dir = c.lane >> 3, u = (c.lane >> 1) & 3;
+    const int w0d = __shfl_sync(0xffffffffu, w0, (dir & 1) << 4);    // w0 of the alpha (lane 0) / beta (lane 16) half
+    if (c.lane < 16 && u < len) l2_discard(c.Yb + (w0d + u) * 16 + (c.lane & 1) * 8);
 }
 
 // One recompute window of the "out" phase (all lanes in natural labels):
@@ -316,21 +336,21 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         __stcg(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
     }
     if (c.isb) slot_put(c.slotX(), c.lane, X);                      // running alpha of the beta lane
-    if (nlen) yq_park(c, nq);
+    if (nlen) yq_park(c, nq, nw0, nlen);
 }
 
 // pass 1, first half, steps [j0, j1) (even count): build this thread's records on the fly (prep
 // fused).  Two steps per iteration: the float64 chains of steps j+2 and j+3 and the float32
 // recursion of steps j and j+1 share one basic block, so the scheduler can interleave them.
 // TMST: records go to TMEM (j < T) / shared memory.  PrepState: records and Lc+La of steps j0, j0+1.
-struct PrepState { float gA[8], gB[8]; double2 YA, YB; int ps; };
+
 __device__ __forceinline__ void prep_load(const Ctx &c, unsigned char *dst, int jn, const float4 *Lsrc,
                                           const int16_t *tbl, bool first)
 {   // loads for the prep of this thread's position of step jn (:507-512, :523-524)
     jn = min(jn, c.M - 1);
     const int kn = c.isb ? c.N - 1 - jn : jn;
-    cpa16_stream(dst, Lsrc + kn * 16 + c.f, c.pol);
-    if (!first) cpa16(dst + 16, c.Le + tbl[kn] * 16 + c.f);
+    cpa16_stream(dst, Lsrc + kn * 16 + c.f, c.pol, c.one);
+    if (!first) cpa16(dst + 16, c.Le + tbl[kn] * 16 + c.f, c.one);
 }
 template <bool FIRST>
 __device__ __forceinline__ void prep_record(const unsigned char *src, float (&g)[8], double2 &Y)
@@ -341,37 +361,45 @@ __device__ __forceinline__ void prep_record(const unsigned char *src, float (&g)
     Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));    // Lc + La (:135)
     make_record(Y.x, Y.y, x.z, x.w, g);
 }
+struct PrepRec { float gA[8], gB[8]; double2 YA, YB; };      // records and Lc+La of two consecutive steps
+struct PrepState { PrepRec r; int ps; };
+// steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 into `out`
+template <bool FIRST, bool TMST>
+__device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *Lsrc, const int16_t *tbl,
+                                            int &ps, const PrepRec &in, PrepRec &out, float (&v)[16])
+{
+    const int N = c.N;
+    unsigned char *slot = c.stage + c.lane * 32 + ps * 2048;
+    cpa_wait<kRingPairs - 1>();
+    prep_record<FIRST>(slot, out.gA, out.YA);                       // clamped at the end: harmless re-computation
+    prep_record<FIRST>(slot + 1024, out.gB, out.YB);
+    prep_load(c, slot, jj + 2 + 2 * kRingPairs, Lsrc, tbl, FIRST);
+    prep_load(c, slot + 1024, jj + 3 + 2 * kRingPairs, Lsrc, tbl, FIRST);
+    cpa_commit();
+    ps = ps == kRingPairs - 1 ? 0 : ps + 1;
+    const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
+    if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
+    else      smem_put(c, k0, in.gA);
+    __stcg(c.Yb + k0 * 16 + c.f, in.YA);
+    pass_step(v, in.gA, c.isb);
+    if (TMST) tm_st8(c.tq + 8u * (jj + 1), in.gB);
+    else      smem_put(c, k1, in.gB);
+    __stcg(c.Yb + k1 * 16 + c.f, in.YB);
+    pass_step(v, in.gB, c.isb);
+}
 template <bool FIRST, bool TMST>
 __device__ __forceinline__ void pass1a_range(const Ctx &c, int j0, int j1, const float4 *Lsrc,
                                              const int16_t *tbl, PrepState &P, float (&v)[16])
 {
-    const int N = c.N;
-    unsigned char *ring = c.stage + c.lane * 32;
-    for (int jj = j0; jj < j1; jj += 2) {
-        // records of steps jj+2, jj+3 (clamped at the end: harmless re-computation)
-        cpa_wait<2>();
-        unsigned char *slot = ring + P.ps * 2048;
-        float gC[8], gD[8];
-        double2 YC, YD;
-        prep_record<FIRST>(slot, gC, YC);
-        prep_record<FIRST>(slot + 1024, gD, YD);
-        prep_load(c, slot, jj + 8, Lsrc, tbl, FIRST);
-        prep_load(c, slot + 1024, jj + 9, Lsrc, tbl, FIRST);
-        cpa_commit();
-        P.ps = P.ps == 2 ? 0 : P.ps + 1;
-        // steps jj, jj+1
-        const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
-        if (TMST) tm_st8(c.tq + 8u * jj, P.gA);
-        else      smem_put(c, k0, P.gA);
-        __stcg(c.Yb + k0 * 16 + c.f, P.YA);
-        pass_step(v, P.gA, c.isb);
-        if (TMST) tm_st8(c.tq + 8u * (jj + 1), P.gB);
-        else      smem_put(c, k1, P.gB);
-        __stcg(c.Yb + k1 * 16 + c.f, P.YB);
-        pass_step(v, P.gB, c.isb);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { P.gA[i] = gC[i]; P.gB[i] = gD[i]; }
-        P.YA = YC; P.YB = YD;
+    PrepRec Q;
+    int jj = j0;
+    for (; jj + 4 <= j1; jj += 4) {                                 // ping-pong: no register copies
+        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, v);
+        pass1a_pair<FIRST, TMST>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, v);
+    }
+    if (jj < j1) {
+        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, v);
+        P.r = Q;
     }
 }
 
@@ -382,17 +410,17 @@ __device__ __forceinline__ void pass1a(const Ctx &c, bool second, float (&v)[16]
     const int16_t *tbl = second ? c.perm : c.inv;                   // La = Le[perm k] (:507-508) / Le[inv k] (:523-524)
     unsigned char *ring = c.stage + c.lane * 32;
 #pragma unroll 1
-    for (int p = 0; p < 3; ++p) {                                   // ring of 3 step pairs
+    for (int p = 0; p < kRingPairs; ++p) {                          // ring of step pairs
         prep_load(c, ring + p * 2048, 2 * p, Lsrc, tbl, FIRST);
         prep_load(c, ring + p * 2048 + 1024, 2 * p + 1, Lsrc, tbl, FIRST);
         cpa_commit();
     }
     PrepState P;
-    cpa_wait<2>();
-    prep_record<FIRST>(ring, P.gA, P.YA);                            // steps 0, 1
-    prep_record<FIRST>(ring + 1024, P.gB, P.YB);
-    prep_load(c, ring, 6, Lsrc, tbl, FIRST);
-    prep_load(c, ring + 1024, 7, Lsrc, tbl, FIRST);
+    cpa_wait<kRingPairs - 1>();
+    prep_record<FIRST>(ring, P.r.gA, P.r.YA);                        // steps 0, 1
+    prep_record<FIRST>(ring + 1024, P.r.gB, P.r.YB);
+    prep_load(c, ring, 2 * kRingPairs, Lsrc, tbl, FIRST);
+    prep_load(c, ring + 1024, 2 * kRingPairs + 1, Lsrc, tbl, FIRST);
     cpa_commit();
     P.ps = 1;
     pass1a_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
@@ -414,6 +442,8 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     else       pass1a<false>(c, second, v);
     tm_wait_st();
     __syncwarp();
+    if (!first && !last)                                            // old extrinsics are dead: every line is rewritten below
+        for (int i = lane; i < N * 2; i += 32) l2_discard(c.Le + i * 8);
     { const long long t = clock64(); ph[1] += t - tA; tA = t; }
     // ---- pass 1, second half: the records the partner lane built ---------------------------
     run_pass<1, false>(c, M, N - T, v);
@@ -428,7 +458,7 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
         yq_load(c, win_w0(0), win_len(0), q0);                      // Y of the first window: arrives during pass 2
         run_pass<0, true>(c, 0, T, v);
         run_pass<1, true>(c, T, M, v);
-        yq_park(c, q0);
+        yq_park(c, q0, win_w0(0), win_len(0));
     }
     { const long long t = clock64(); ph[3] += t - tA; tA = t; }
     // ---- crossing: the half-warps swap chains (beta lanes back to natural labels): every lane
@@ -446,6 +476,7 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     for (int i = 0; i < nwin; ++i) {
         cpa_wait<0>();
         __syncwarp();
+        if (lane < 16) l2_discard(c.CK + (i * 4 + (lane >> 2)) * 32 + (lane & 3) * 8);   // 16 lines, one each
         const int wa = i < nfull ? M - (i + 1) * kW : 0;
         const int nlen = i + 1 < nwin ? win_len(i + 1) : 0;
         const int nw0 = i + 1 < nwin ? win_w0(i + 1) : 0;
@@ -490,9 +521,10 @@ tpf_kernel(const TpfArgs A)
     {   // ptxas folds a warp-uniform base into a [R+UR+imm] shared-memory operand; for LDGSTS (cp.async)
         // that form raises "illegal instruction" on sm_100a, so the staging base goes through memory
         volatile unsigned *slots = reinterpret_cast<volatile unsigned *>(smem_raw + tab_bytes);
-        if (lane == 0) slots[4 + warp] = (unsigned)warp * kStageBytes;
+        if (lane == 0) { slots[4 + warp] = (unsigned)warp * kStageBytes; slots[1] = 1u; }
         __syncwarp();
         c.stage = stage_all + slots[4 + warp];
+        c.one = slots[1];
         __syncwarp();
     }
     c.perm = tab; c.inv = tab + N;
@@ -513,8 +545,65 @@ tpf_kernel(const TpfArgs A)
     for (int tile = wg; tile < A.n_tiles; tile += gridDim.x * kTpfWarps) {
         const long long frame0 = (long long)tile * kTpfFrames;
         const long long t0 = clock64();
-        // ---- de-puncture + transpose the 16 frames' LLRs into [k][frame] (:466-487, :507-512);
-        //      lane <-> k, 8 frames' loads in flight at a time ---------------------------------
+        // ---- de-puncture + transpose the 16 frames' LLRs into [k][frame] (:466-487, :507-512).
+        //      Each frame's row is pulled into the staging area with coalesced 16-byte loads
+        //      (every line of the input is read exactly once), two frames in flight; the lanes
+        //      then pick their couples (and the permuted systematic pair) out of shared memory.
+        if (A.vec4) {
+            float *rowbuf = reinterpret_cast<float *>(c.stage);
+            const int nq = (A.n_llr + 3) / 4;                       // float4 per row (row pitch is a multiple of 16 B)
+            auto pull = [&](int fr) {
+                const long long frame = frame0 + fr;
+                if (frame < A.B) {
+                    const float4 *src = reinterpret_cast<const float4 *>(A.llr + frame * A.llr_stride);
+                    float4 *dst = reinterpret_cast<float4 *>(rowbuf + (fr & 1) * kRowFloats);
+                    for (int i = lane; i < nq; i += 32) cpa16_stream(dst + i, src + i, c.pol, c.one);
+                }
+                cpa_commit();
+            };
+            pull(0);
+            // this lane's couples k = lane + 32 i: stream offsets read once per tile, not once per frame
+            constexpr int kMaxK = 8;                                // N <= 256
+            short oa[kMaxK], op[kMaxK], o0[kMaxK], o1[kMaxK], o2[kMaxK], o3[kMaxK];
+#pragma unroll
+            for (int i = 0; i < kMaxK; ++i) {
+                const int k = min(lane + 32 * i, N - 1);
+                oa[i] = __ldg(g_off + k); op[i] = __ldg(g_off + c.perm[k]);
+                o0[i] = __ldg(g_off + N + k); o1[i] = __ldg(g_off + 2 * N + k);
+                o2[i] = __ldg(g_off + 3 * N + k); o3[i] = __ldg(g_off + 4 * N + k);
+            }
+            if (A.ref_bits) {                                       // the hard decision will want these rows in L2
+                const int lines = (2 * N * kTpfFrames + 127) / 128;
+                const long long nb = min((long long)kTpfFrames, A.B - frame0) * 2 * N;
+                for (int i = lane; i < lines; i += 32)
+                    if ((long long)i * 128 < nb) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.ref_bits + frame0 * 2 * N + i * 128));
+            }
+            for (int fr = 0; fr < kTpfFrames; ++fr) {
+                if (fr + 1 < kTpfFrames) pull(fr + 1); else cpa_commit();
+                cpa_wait<1>();
+                __syncwarp();
+                const float *row = rowbuf + (fr & 1) * kRowFloats;
+                const bool livef = frame0 + fr < A.B;
+#pragma unroll
+                for (int i = 0; i < kMaxK; ++i) {
+                    const int k = lane + 32 * i;
+                    if (k < N) {
+                        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f), x2 = x1;
+                        if (livef) {
+                            x1.x = row[oa[i]]; x1.y = row[oa[i] + 1]; x2.x = row[op[i]]; x2.y = row[op[i] + 1];
+                            if (o0[i] >= 0) x1.z = row[o0[i]];
+                            if (o1[i] >= 0) x1.w = row[o1[i]];
+                            if (o2[i] >= 0) x2.z = row[o2[i]];
+                            if (o3[i] >= 0) x2.w = row[o3[i]];
+                        }
+                        __stcg(c.L1A + k * 16 + fr, x1);
+                        __stcg(c.L2A + k * 16 + fr, x2);
+                    }
+                }
+                __syncwarp();
+            }
+            cpa_wait<0>();
+        } else
         for (int k = lane; k < N; k += 32) {
             const int oa = __ldg(g_off + k), op = __ldg(g_off + c.perm[k]);
             const int o0 = __ldg(g_off + N + k), o1 = __ldg(g_off + 2 * N + k);
@@ -540,17 +629,6 @@ tpf_kernel(const TpfArgs A)
                 for (int fr = 0; fr < 8; ++fr) {
                     __stcg(c.L1A + k * 16 + f0 + fr, x1[fr]);
                     __stcg(c.L2A + k * 16 + f0 + fr, x2[fr]);
-                }
-            }
-        }
-        if (A.prefetch) {   // pull the next tile's rows into L2 while this one decodes
-            const long long nf0 = frame0 + (long long)gridDim.x * kTpfWarps * kTpfFrames;
-            const int lines = (A.n_llr * 4 + 127) / 128;
-            for (int i = lane; i < kTpfFrames * lines; i += 32) {
-                const long long frame = nf0 + i / lines;
-                if (frame < A.B) {
-                    const float *pl = A.llr + frame * A.llr_stride + (i % lines) * 32;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
                 }
             }
         }
@@ -710,9 +788,9 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     A.g = c.tpf; A.B = B; A.iterations = c.iterations;
     A.n_tiles = (B + kTpfFrames - 1) / kTpfFrames;
     A.n_llr = c.n_llr;
-    A.prefetch = getenv("B200DVB_PREFETCH") ? atoi(getenv("B200DVB_PREFETCH")) : 0;
-    A.vec = c.vec_ab && c.vec_wy && (llr_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 7) == 0);
-    if (getenv("B200DVB_NOVEC")) A.vec = 0;
+    // whole rows by 16-byte cp.async: pitch and base 16-byte aligned, row fits half the staging area
+    A.vec4 = (c.N <= 256) && (llr_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && ((c.n_llr + 3) / 4 * 4 <= kRowFloats) &&
+             !getenv("B200DVB_NOVEC4");
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;

@@ -197,8 +197,8 @@ TPF_HD void ext_step(float (&x)[16], const float (&zs)[16], const float (&g)[8],
 // Extrinsic epilogue for one step (dvb_rcs2_turbo.py:250-279).
 TPF_HD void make_extrinsic(const float (&uv)[4], double YA, double YB, double sf, double &ea, double &eb)
 {
-    const double a = d_mul(YA, 0.5), b = d_mul(YB, 0.5);
-    const bool sP = d_add(a, b) < 0.0, sM = d_sub(a, b) < 0.0;
+    // sign of fl(YA/2 + YB/2) == sign of fl(YA + YB): halving commutes with rounding
+    const bool sP = d_add(YA, YB) < 0.0, sM = d_sub(YA, YB) < 0.0;
     const float app0 = sP ? uv[1] : uv[0], app3 = sP ? uv[0] : uv[1];
     const float app1 = sM ? uv[3] : uv[2], app2 = sM ? uv[2] : uv[3];
     const float LA = f_sub(f_max(app0, app1), f_max(app2, app3));

@@ -198,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
     gbps = frames_per_s * codec.k_info / 1e9
     cnt = counters.cpu().numpy()
 
-    # ---- roofline of the dominant kernel (quad_kernel<false>, one launch per step) ----
+    # ---- roofline of the dominant kernel (tpf_kernel, the thread-per-frame decoder; one launch per step) ----
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     clocks = clk.summary()
     mp = measured_peaks()
@@ -209,18 +209,22 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     try:        # DRAM bytes of this kernel from the committed `ncu --set full` capture, scaled per frame
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = tr["quad_bytes_per_frame"] * B
+        traffic = tr["tpf_bytes_per_frame"] * B
     except Exception:
         pass
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_quad_ncu.txt: 8 373 B/frame at 65 536 "
+            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 106 993 B/frame at 65 536 "
                             "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
-                            "reference bits in)",
+                            "reference bits in). The rest is decoder scratch that does not fit the 126 MB L2 with 64 "
+                            "frames per SM in flight: the transposed channel LLRs are re-read every half-iteration "
+                            "(3 392 B x 16) and the extrinsics are written back between half-iterations; dead scratch "
+                            "lines are dropped with discard.global.L2 (was 237 KB/frame without). 12 % of HBM peak.",
             "note": "ACS = add-compare-select of the reference algorithm (320*N per SISO, SURVEY 8d); peak = "
                     "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at "
-                    "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). HBM traffic of the kernel "
-                    "is < 1% of the copy peak, so MEASURED_PEAKS.json has no denominator for it.",
+                    "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). The kernel is bound by "
+                    "instruction issue (ncu: 55 % issue-active with one warp per scheduler), not by HBM (12 % of the "
+                    "copy peak), so MEASURED_PEAKS.json has no denominator for it.",
             "frac_at_measured_clock": (achieved / (NOMINAL_ACS_PER_CLK_SM * sms * clocks["sm_mhz"] * 1e6 / 1e12))
             if clocks.get("sm_mhz") else None}
 

@@ -259,8 +259,30 @@ def max_log_map_decode(*args):
 # ---------------------------------------------------------------------------
 # DVBRCS2_Turbo (dvb_rcs2_turbo.py:287-537)
 # ---------------------------------------------------------------------------
+def bijective_interleaver(N):
+    """An almost-regular-permutation interleaver that IS a permutation (extension for non-parity runs):
+    pi(i) = (P i + 4 d(i mod 4) + 3) mod N with P the table's period made coprime to N."""
+    from math import gcd
+    P = INTERLEAVER_PARAMS[N][0] if N in INTERLEAVER_PARAMS else 13
+    while gcd(P, N) != 1:
+        P += 2
+    i = np.arange(N, dtype=np.int64)
+    d = np.array([0, 3, 5, 2], dtype=np.int64)[i % 4]
+    perm = ((P * i + 4 * d + 3) % N).astype(np.int32)
+    while len(np.unique(perm)) != N:                          # 4 d(i mod 4) keeps residues apart unless 4 | P's orbit
+        P += 2
+        while gcd(P, N) != 1:
+            P += 2
+        perm = ((P * i + 4 * d + 3) % N).astype(np.int32)
+    return perm
+
+
 class DVBRCS2_Turbo:
-    def __init__(self, N_couples, code_rate, iterations=8):
+    def __init__(self, N_couples, code_rate, iterations=8, perm=None):
+        """``perm`` (extension, NOT reference behaviour): a user-supplied interleaver table of length N
+        replacing the committed one, whose formula is not a permutation (BER ~ 0.2 at every
+        SNR).  With a bijective ``perm`` the same kernels decode properly; results are then compared with
+        the oracle given the same table, and reported as a labelled non-parity run."""
         self.N = N_couples
         self.k_info = N_couples * 2
         self.iterations = iterations
@@ -268,6 +290,12 @@ class DVBRCS2_Turbo:
         if self.N not in INTERLEAVER_PARAMS:                    # :295-296
             raise ValueError(f"Block size {self.N} not in standard tables.")
         self._init_interleaver()
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, np.int32)
+            if perm.shape != (self.N,) or perm.min() < 0 or perm.max() >= self.N:
+                raise ValueError("perm must hold N indices in [0, N)")
+            self.perm = perm
+            self.inv_perm = np.argsort(self.perm).astype(np.int32)
         for k, v in _trellis_tables().items():
             setattr(self, k, v)
         self._calc_coded_size()

@@ -74,6 +74,9 @@ int b200dvb_codec_destroy(b200dvb_codec_t codec);
 /* LLRs the depuncturer consumes per frame (= bits the encoder emits; differs
  * from the reference's n_coded when N % period != 0, dvb_rcs2_turbo.py:398-402) */
 int b200dvb_codec_n_llr(b200dvb_codec_t codec);
+/* Frames the decode kernel keeps resident at a time on this device (one "wave": SMs x frames per SM).
+ * Batches and pipeline chunks that are multiples of it leave no SM idle in the last wave. */
+int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec);
 
 /* One SISO half-iteration for B independent frames.  Replaces bcjr_max_log_map
  * (dvb_rcs2_turbo.py:116-281; historic aliases bcjr_decode_circular /

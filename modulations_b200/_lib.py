@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200dvb_codec_create": (_c_int, [_c_int] + [_c_void_p] * 6 + [_c_int, _c_int, _c_double, _c_double, _c_void_p]),
     "b200dvb_codec_destroy": (_c_int, [_c_void_p]),
     "b200dvb_codec_n_llr": (_c_int, [_c_void_p]),
+    "b200dvb_codec_frames_per_wave": (_c_int, [_c_void_p]),
     "b200dvb_codec_circular_lut": (_c_int, [_c_void_p, _c_void_p]),
     "b200dvb_siso_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "b200dvb_siso": (_c_int, [_c_void_p, _c_int] + [_c_void_p] * 6 + [_c_double] + [_c_void_p] * 3 + [_c_size_t, _c_void_p]),

@@ -201,6 +201,14 @@ int b200dvb_codec_destroy(b200dvb_codec_t codec)
 
 int b200dvb_codec_n_llr(b200dvb_codec_t codec) { return codec ? codec->c.n_llr : B200DVB_EINVAL; }
 
+int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec)
+{
+    if (!codec) return B200DVB_EINVAL;
+    const Codec &c = codec->c;
+    if (c.tpf.enabled) return c.num_sms * kTpfWarps * kTpfFrames;
+    return c.num_sms * c.geom.ctas_per_sm * c.geom.frames;
+}
+
 int b200dvb_codec_circular_lut(b200dvb_codec_t codec, int32_t *lut16_h)
 {
     if (!codec || !lut16_h) return B200DVB_EINVAL;

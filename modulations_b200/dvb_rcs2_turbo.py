@@ -394,7 +394,7 @@ class DVBRCS2_Turbo:
             res = res.cpu().numpy()
         return res
 
-    def decode_batch_host(self, llr_host, out_host=None, chunk=32768):
+    def decode_batch_host(self, llr_host, out_host=None, chunk=None):
         """End-to-end decode of HOST buffers: pinned ``llr_host`` float32 [B, n_llr] ->
         pinned ``out_host`` int32 [B, 2N].  Chunks are pipelined over three CUDA streams
         so the host->device copy of chunk i+1, the decode of chunk i and the

@@ -244,7 +244,7 @@ __device__ __forceinline__ void yq_load(const Ctx &c, int w0, int len, YQ &q)
 #pragma unroll
     for (int u = 0; u < kW; ++u) q.y[u] = __ldcg(c.Yb + (w0 + min(u, len - 1)) * 16 + c.f);
 }
-__device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int len)
+__device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int len, int ck_slot)
 {
 
 #pragma unroll
@@ -253,11 +253,14 @@ __device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int l
                      :: "r"(c.tq + c.ycol + 4u * u), "r"(__double2loint(q.y[u].x)), "r"(__double2hiint(q.y[u].x)),
                         "r"(__double2loint(q.y[u].y)), "r"(__double2hiint(q.y[u].y)) : "memory");
     tm_wait_st();
-    // the values are in TMEM now.  The window's Y of both half-warps are 2 x len x 2 lines of 128 bytes:
-    // one predicated discard instruction, lane = (half-warp, step, half line)
-    const int dir = c.lane >> 3, u = (c.lane >> 1) & 3;
-    const int w0d = __shfl_sync(0xffffffffu, w0, (dir & 1) << 4);    // w0 of the alpha (lane 0) / beta (lane 16) half
-    if (c.lane < 16 && u < len) l2_discard(c.Yb + (w0d + u) * 16 + (c.lane & 1) * 8);
+    // the values are in TMEM now.  ONE predicated discard instruction drops the dead scratch of this window:
+    // lanes 0-15 the 2 x len x 2 lines of Y (lane = half-warp, step, half line), lanes 16-31 the 16 lines of
+    // the checkpoint slot the window consumed
+    const int dir = (c.lane >> 3) & 1, u = (c.lane >> 1) & 3, l16 = c.lane & 15;
+    const int w0d = __shfl_sync(0xffffffffu, w0, dir << 4);         // w0 of the alpha (lane 0) / beta (lane 16) half
+    const void *line = c.lane < 16 ? static_cast<const void *>(c.Yb + (w0d + u) * 16 + (c.lane & 1) * 8)
+                                   : static_cast<const void *>(c.CK + (ck_slot * 4 + (l16 >> 2)) * 32 + (l16 & 3) * 8);
+    if (c.lane < 16 ? u < len : ck_slot >= 0) l2_discard(line);
 }
 
 // One recompute window of the "out" phase (all lanes in natural labels):
@@ -336,7 +339,7 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         __stcg(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
     }
     if (c.isb) slot_put(c.slotX(), c.lane, X);                      // running alpha of the beta lane
-    if (nlen) yq_park(c, nq, nw0, nlen);
+    if (nlen) yq_park(c, nq, nw0, nlen, nslot - 1);
 }
 
 // pass 1, first half, steps [j0, j1) (even count): build this thread's records on the fly (prep
@@ -458,7 +461,7 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
         yq_load(c, win_w0(0), win_len(0), q0);                      // Y of the first window: arrives during pass 2
         run_pass<0, true>(c, 0, T, v);
         run_pass<1, true>(c, T, M, v);
-        yq_park(c, q0, win_w0(0), win_len(0));
+        yq_park(c, q0, win_w0(0), win_len(0), -1);
     }
     { const long long t = clock64(); ph[3] += t - tA; tA = t; }
     // ---- crossing: the half-warps swap chains (beta lanes back to natural labels): every lane
@@ -476,7 +479,6 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     for (int i = 0; i < nwin; ++i) {
         cpa_wait<0>();
         __syncwarp();
-        if (lane < 16) l2_discard(c.CK + (i * 4 + (lane >> 2)) * 32 + (lane & 3) * 8);   // 16 lines, one each
         const int wa = i < nfull ? M - (i + 1) * kW : 0;
         const int nlen = i + 1 < nwin ? win_len(i + 1) : 0;
         const int nw0 = i + 1 < nwin ? win_w0(i + 1) : 0;

@@ -398,9 +398,14 @@ class DVBRCS2_Turbo:
         """End-to-end decode of HOST buffers: pinned ``llr_host`` float32 [B, n_llr] ->
         pinned ``out_host`` int32 [B, 2N].  Chunks are pipelined over three CUDA streams
         so the host->device copy of chunk i+1, the decode of chunk i and the
-        device->host copy of chunk i-1 overlap.  Returns out_host (a torch CPU tensor)."""
+        device->host copy of chunk i-1 overlap.  ``chunk`` defaults to one wave of the decode
+        kernel (measured best on the B200, tools/e2e_chunks.py: filling and draining the pipeline
+        costs one chunk's copies, and a whole wave leaves no SM idle).  Returns out_host (a torch
+        CPU tensor)."""
         torch = _lib.require_cuda()
         h = self.handle
+        if chunk is None:
+            chunk = max(16, int(_lib.load().b200dvb_codec_frames_per_wave(h.h)))
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(llr_host, np.float32))
         if x.dim() != 2 or x.shape[1] < h.n_llr:
             raise IndexError(f"llr needs shape [B, >= {h.n_llr}]")

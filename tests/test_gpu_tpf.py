@@ -86,3 +86,24 @@ def test_tpf_large_batch_is_position_independent():
     dec = g.decode_batch(big).reshape(reps, 24, 2 * N)
     want = torch.from_numpy(ref).cuda()
     assert bool((dec == want[None]).all())
+
+
+@pytest.mark.parametrize("chunk", [None, 1000, 4096])
+def test_host_pipeline_matches_resident_decode(chunk):
+    """decode_batch_host (pinned host in -> pinned host out, 3-stream pipeline; the call bench.py's e2e
+    figure times) must return exactly what the resident decode returns, for the default chunk (one kernel
+    wave) and for chunks that do not divide the batch."""
+    import torch
+    N, rate, iters = 48, '1/3', 2
+    o = oracle.OracleTurbo(N, rate, iters)
+    info, llr = _llrs(o, N, rate, 16, 2.0, 11)
+    g = _codec(N, rate, iters, "tpf")
+    B = 21000                                    # more than two default chunks (9 472 frames on a B200)
+    reps = (B + 15) // 16
+    big = torch.from_numpy(llr).repeat(reps, 1)[:B].contiguous().pin_memory()
+    want = g.decode_batch(big.cuda())
+    out = g.decode_batch_host(big) if chunk is None else g.decode_batch_host(big, chunk=chunk)
+    assert out.dtype == torch.int32 and tuple(out.shape) == (B, 2 * N)
+    assert bool((out.cuda() == want).all())
+    ref = torch.from_numpy(o.decode_batch(llr))
+    assert bool((out[:16] == ref).all())

@@ -12,4 +12,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tpf_kernel -s 1 -c 1 -o gpurun_out/prof_tpf_full python tools/tpf_perf.py 65536 > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/prof_tpf_full.ncu-rep --page raw --csv > gpurun_out/tpf_full_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_tpf_full.ncu-rep --page source --csv > gpurun_out/tpf_full_src.csv 2>/dev/null
+timeout 300 python tools/tpf_perf.py 262144 48 > gpurun_out/tpf_perf_final.txt 2>&1; cat gpurun_out/tpf_perf_final.txt
 ls -la gpurun_out | tail -12

@@ -214,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 106 993 B/frame at 65 536 "
+            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 108 693 B/frame at 65 536 "
                             "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
                             "reference bits in). The rest is decoder scratch that does not fit the 126 MB L2 with 64 "
                             "frames per SM in flight: the transposed channel LLRs are re-read every half-iteration "

@@ -131,7 +131,7 @@ struct Ctx {
     unsigned char *stage;            // this warp's staging area (kStageBytes)
     const int16_t *perm, *inv;       // shared-memory copies of the interleaver tables
     float4 *L1A, *L2A;               // de-punctured channel LLRs [k][16]: (A,B,W1,Y1)[k] and (A,B)[perm k],(W2,Y2)[k]
-    double2 *Le, *LeF, *Yb;          // extrinsics (in place; last half-iteration -> LeF) and Y = Lc + La, [k][16]
+    double2 *Le, *LeF, *Yb;          // extrinsics [k][16] (in place; last half-iteration -> LeF); Y = Lc + La, [k/2][16] x 32 B
     float4 *CK;                      // checkpoints [slot][4][32 lanes]
     unsigned long long pol;          // L2 evict-first policy for the channel LLRs
     unsigned one;                    // 1, opaque to the compiler (see cpa16)
@@ -238,11 +238,26 @@ __device__ __forceinline__ void tm_wait_ld4(float (&y)[4])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(y[0]), "+f"(y[1]), "+f"(y[2]), "+f"(y[3]) :: "memory");
 }
+// Y = Lc + La travels in 32-byte entries: the two steps of a pair, in ascending k, per lane.  256-bit global
+// accesses (sm_100: LDG/STG.E.ENL2.256): one instruction per pair instead of two.  Layout [k/2][16 frames].
+__device__ __forceinline__ void st256_f64(void *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256_f64(const void *p, double2 &lo, double2 &hi)
+{
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned char *y_entry(const Ctx &c, int k_even)
+{
+    return reinterpret_cast<unsigned char *>(c.Yb) + ((size_t)(k_even >> 1) * 16 + c.f) * 32;
+}
 struct YQ { double2 y[kW]; };
 __device__ __forceinline__ void yq_load(const Ctx &c, int w0, int len, YQ &q)
 {   // global loads issued a whole window ahead of their use
-#pragma unroll
-    for (int u = 0; u < kW; ++u) q.y[u] = __ldcg(c.Yb + (w0 + min(u, len - 1)) * 16 + c.f);
+    static_assert(kW == 4, "two 32-byte entries per window");
+    ld256_f64(y_entry(c, w0), q.y[0], q.y[1]);                      // w0 is even for both half-warps
+    ld256_f64(y_entry(c, len > 2 ? w0 + 2 : w0), q.y[2], q.y[3]);
 }
 __device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int len, int ck_slot)
 {
@@ -256,11 +271,12 @@ __device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int l
     // the values are in TMEM now.  ONE predicated discard instruction drops the dead scratch of this window:
     // lanes 0-15 the 2 x len x 2 lines of Y (lane = half-warp, step, half line), lanes 16-31 the 16 lines of
     // the checkpoint slot the window consumed
-    const int dir = (c.lane >> 3) & 1, u = (c.lane >> 1) & 3, l16 = c.lane & 15;
+    const int dir = (c.lane >> 3) & 1, pr = (c.lane >> 2) & 1, l16 = c.lane & 15;
     const int w0d = __shfl_sync(0xffffffffu, w0, dir << 4);         // w0 of the alpha (lane 0) / beta (lane 16) half
-    const void *line = c.lane < 16 ? static_cast<const void *>(c.Yb + (w0d + u) * 16 + (c.lane & 1) * 8)
-                                   : static_cast<const void *>(c.CK + (ck_slot * 4 + (l16 >> 2)) * 32 + (l16 & 3) * 8);
-    if (c.lane < 16 ? u < len : ck_slot >= 0) l2_discard(line);
+    const void *line = c.lane < 16
+        ? static_cast<const void *>(reinterpret_cast<const unsigned char *>(c.Yb) + ((size_t)((w0d >> 1) + pr) * 16) * 32 + (c.lane & 3) * 128)
+        : static_cast<const void *>(c.CK + (ck_slot * 4 + (l16 >> 2)) * 32 + (l16 & 3) * 8);
+    if (c.lane < 16 ? 2 * pr < len : ck_slot >= 0) l2_discard(line);
 }
 
 // One recompute window of the "out" phase (all lanes in natural labels):
@@ -383,11 +399,12 @@ __device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *
     const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
     if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
     else      smem_put(c, k0, in.gA);
-    __stcg(c.Yb + k0 * 16 + c.f, in.YA);
+    // both steps' Y in one 256-bit store, ascending k (the beta lane walks k downwards: swap)
+    st256_f64(y_entry(c, c.isb ? k1 : k0), c.isb ? in.YB.x : in.YA.x, c.isb ? in.YB.y : in.YA.y,
+              c.isb ? in.YA.x : in.YB.x, c.isb ? in.YA.y : in.YB.y);
     pass_step(v, in.gA, c.isb);
     if (TMST) tm_st8(c.tq + 8u * (jj + 1), in.gB);
     else      smem_put(c, k1, in.gB);
-    __stcg(c.Yb + k1 * 16 + c.f, in.YB);
     pass_step(v, in.gB, c.isb);
 }
 template <bool FIRST, bool TMST>

@@ -116,7 +116,15 @@ __device__ __forceinline__ void l2_discard(const void *line128)
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(line128) : "memory");
 }
 
-constexpr int kRingPairs = 4;        // pass-1 prefetch ring depth in step pairs (2 KB each: the whole beta-vector area)
+#ifdef TPF_WEAK_ALL
+template <typename T> __device__ __forceinline__ void st_ws(T *p, const T &v) { *p = v; }
+#else
+template <typename T> __device__ __forceinline__ void st_ws(T *p, const T &v) { __stcg(p, v); }
+#endif
+#ifndef TPF_RING
+#define TPF_RING 4
+#endif
+constexpr int kRingPairs = TPF_RING;        // pass-1 prefetch ring depth in step pairs (2 KB each: the whole beta-vector area)
 // per-warp staging area: [0, 8K) beta vectors of the current window, [kW][4][32] float4 (the
 // pass-1 prefetch ring, 6 KB, aliases it); [8K, 10K) Z slot; [10K, 12K) X slot
 constexpr int kStageBytes = 12288;
@@ -135,6 +143,7 @@ struct Ctx {
     float4 *CK;                      // checkpoints [slot][4][32 lanes]
     unsigned long long pol;          // L2 evict-first policy for the channel LLRs
     unsigned one;                    // 1, opaque to the compiler (see cpa16)
+    mutable unsigned junk;           // sink of the operand-hold instructions (see hold_until)
     __device__ __forceinline__ float4 *wstore() const { return reinterpret_cast<float4 *>(stage); }
     __device__ __forceinline__ float4 *slotZ() const { return reinterpret_cast<float4 *>(stage + 8192); }
     __device__ __forceinline__ float4 *slotX() const { return reinterpret_cast<float4 *>(stage + 10240); }
@@ -181,7 +190,7 @@ __device__ __forceinline__ void ck_store(const Ctx &c, int slot, const float (&v
     for (int s = 0; s < 16; ++s) n[s] = c.isb ? v[rho4(s)] : v[s];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        __stcg(c.CK + (slot * 4 + q) * 32 + c.lane, make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]));
+        st_ws(c.CK + (slot * 4 + q) * 32 + c.lane, make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]));
 }
 
 // steps [j0, j1) of an "in" pass (j1 - j0 even), records of storage class KIND; CKPT: store a
@@ -242,7 +251,11 @@ __device__ __forceinline__ void tm_wait_ld4(float (&y)[4])
 // accesses (sm_100: LDG/STG.E.ENL2.256): one instruction per pair instead of two.  Layout [k/2][16 frames].
 __device__ __forceinline__ void st256_f64(void *p, double a, double b, double c, double d)
 {
+#if defined(TPF_WEAK_Y) || defined(TPF_WEAK_ALL)
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
     asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
 }
 __device__ __forceinline__ void ld256_f64(const void *p, double2 &lo, double2 &hi)
 {
@@ -342,7 +355,7 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         double ea, eb;                                              // epilogue of step u-1
         make_extrinsic(uvp, __hiloint2double(__float_as_int(yr[1]), __float_as_int(yr[0])),
                        __hiloint2double(__float_as_int(yr[3]), __float_as_int(yr[2])), sf, ea, eb);
-        __stcg(LeOut + (w0 + u - 1) * 16 + c.f, make_double2(ea, eb));
+        st_ws(LeOut + (w0 + u - 1) * 16 + c.f, make_double2(ea, eb));
         tm_wait_ld4(yn);
         complete(g);
 #pragma unroll
@@ -352,7 +365,7 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         double ea, eb;
         make_extrinsic(uvp, __hiloint2double(__float_as_int(yr[1]), __float_as_int(yr[0])),
                        __hiloint2double(__float_as_int(yr[3]), __float_as_int(yr[2])), sf, ea, eb);
-        __stcg(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
+        st_ws(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
     }
     if (c.isb) slot_put(c.slotX(), c.lane, X);                      // running alpha of the beta lane
     if (nlen) yq_park(c, nq, nw0, nlen, nslot - 1);
@@ -363,63 +376,172 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
 // recursion of steps j and j+1 share one basic block, so the scheduler can interleave them.
 // TMST: records go to TMEM (j < T) / shared memory.  PrepState: records and Lc+La of steps j0, j0+1.
 
-__device__ __forceinline__ void prep_load(const Ctx &c, unsigned char *dst, int jn, const float4 *Lsrc,
-                                          const int16_t *tbl, bool first)
-{   // loads for the prep of this thread's position of step jn (:507-512, :523-524)
-    jn = min(jn, c.M - 1);
-    const int kn = c.isb ? c.N - 1 - jn : jn;
-    cpa16_stream(dst, Lsrc + kn * 16 + c.f, c.pol, c.one);
-    if (!first) cpa16(dst + 16, c.Le + tbl[kn] * 16 + c.f, c.one);
-}
-template <bool FIRST>
-__device__ __forceinline__ void prep_record(const unsigned char *src, float (&g)[8], double2 &Y)
+// Channel LLRs live in the workspace as [j][32 lanes] float4: lanes 0-15 hold step k = j of frames 0-15, lanes
+// 16-31 step k = N-1-j.  Pass 1a (the only streaming reader) fetches position j of ALL lanes from one 512-byte
+// run, and the two steps of a pair are an immediate 512 bytes apart: one address register per pair.
+__device__ __forceinline__ int lpos(const Ctx &c, int k, int fr) { return k < c.M ? k * 32 + fr : (c.N - 1 - k) * 32 + 16 + fr; }
+
+// cp.async with immediate offsets on both addresses: the four copies of a step pair share ONE destination
+// register (and the two channel copies one source register).  A register that a cp.async reads stays busy
+// for ~20 cycles after issue; ptxas re-used the per-copy address temporaries at once and the lone warp of
+// the sub-partition sat in a write-after-read stall after every copy (profiles/r01_tpf_stalls.txt).
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void cpa16_off(unsigned d, const void *src)
 {
-    const float4 x = *reinterpret_cast<const float4 *>(src);
-    double2 la = make_double2(0.0, 0.0);
-    if (!FIRST) la = *reinterpret_cast<const double2 *>(src + 16);
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(d), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void cpa16_stream_off(unsigned d, const void *src, unsigned long long pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0+%3], [%1+%4], 16, %2;"
+                 ::"r"(d), "l"(src), "l"(pol), "n"(DOFF), "n"(SOFF) : "memory");
+}
+// interleaver entries of this thread's positions of steps jn, jn+1 (jn even), looked up a whole pair before the
+// gather that needs them: a shared-memory load issued behind the ring traffic takes 60-130 cycles to return
+struct Idx { int a, b; };
+__device__ __forceinline__ void idx_get(const Ctx &c, int jn, const int16_t *tbl, Idx &x)
+{
+    jn = min(jn, c.M - 2);
+    const int k0 = c.isb ? c.N - 1 - jn : jn, k1 = c.isb ? k0 - 1 : k0 + 1;
+    x.a = tbl[k0]; x.b = tbl[k1];
+}
+// A memory instruction reads its register operands when it leaves the MIO queue, tens of cycles after issue; a
+// write to one of them before that stalls the lone warp (long-scoreboard write-after-read).  ptxas re-uses such
+// registers at once.  hold_until() keeps the operands LIVE until `late` has been computed: XORs that depend on
+// `late`, accumulated into a sink the compiler cannot drop — a handful of issue slots instead of the stalls.
+struct Held { unsigned r[7]; };
+__device__ __forceinline__ void hold_until(const Ctx &c, float late, const Held &h)
+{
+    unsigned acc;
+    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(acc) : "r"(c.junk), "r"(__float_as_uint(late)), "r"(h.r[0]));
+#pragma unroll
+    for (int i = 1; i < 7; i += 2)
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(acc) : "r"(h.r[i]), "r"(h.r[i + 1]));
+    c.junk = acc;
+}
+__device__ __forceinline__ unsigned lo32(const void *p) { return (unsigned)reinterpret_cast<unsigned long long>(p); }
+__device__ __forceinline__ unsigned hi32(const void *p) { return (unsigned)(reinterpret_cast<unsigned long long>(p) >> 32); }
+// loads for the prep of this thread's positions of steps jn, jn+1 (jn even) (:507-512, :523-524)
+__device__ __forceinline__ void prep_load_pair(const Ctx &c, unsigned char *slot, int jn, const float4 *Lsrc,
+                                               const Idx &x, bool first, Held &h)
+{
+    jn = min(jn, c.M - 2);                                          // clamped at the end: harmless re-computation
+    const unsigned d = s_addr(slot) * c.one;
+    const float4 *src = Lsrc + jn * 32 + c.lane;
+    cpa16_stream_off<0, 0>(d, src, c.pol);
+    cpa16_stream_off<1024, 512>(d, src, c.pol);   // ring slot: [x A][la A][x B][la B], 512 B each, lane-major (conflict-free)
+    h.r[0] = d; h.r[1] = lo32(src); h.r[2] = hi32(src);
+    h.r[3] = h.r[4] = h.r[5] = h.r[6] = 0;
+    if (!first) {
+        const double2 *pa = c.Le + x.a * 16 + c.f, *pb = c.Le + x.b * 16 + c.f;
+        cpa16_off<512, 0>(d, pa);
+        cpa16_off<1536, 0>(d, pb);
+        h.r[3] = lo32(pa); h.r[4] = hi32(pa); h.r[5] = lo32(pb); h.r[6] = hi32(pb);
+    }
+}
+// raw inputs of a step pair, read out of the ring a whole pair before they are needed: the shared-memory
+// load that follows a cp.async wait is ~60 cycles away for a warp with nothing else to run
+struct Raw { float4 xA, xB; double2 laA, laB; };
+template <bool FIRST>
+__device__ __forceinline__ void raw_get(const unsigned char *slot, Raw &r)
+{
+    r.xA = *reinterpret_cast<const float4 *>(slot);
+    r.xB = *reinterpret_cast<const float4 *>(slot + 1024);
+    r.laA = r.laB = make_double2(0.0, 0.0);
+    if (!FIRST) {
+        r.laA = *reinterpret_cast<const double2 *>(slot + 512);
+        r.laB = *reinterpret_cast<const double2 *>(slot + 1536);
+    }
+}
+__device__ __forceinline__ void prep_record(const float4 &x, const double2 &la, float (&g)[8], double2 &Y)
+{
     Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));    // Lc + La (:135)
     make_record(Y.x, Y.y, x.z, x.w, g);
 }
 struct PrepRec { float gA[8], gB[8]; double2 YA, YB; };      // records and Lc+La of two consecutive steps
-struct PrepState { PrepRec r; int ps; };
-// steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 into `out`
+struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; };
+// steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 (raw inputs `rin`) into
+// `out` and pulls the raw inputs of steps jj+4, jj+5 out of the ring into `rout`
 template <bool FIRST, bool TMST>
 __device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *Lsrc, const int16_t *tbl,
-                                            int &ps, const PrepRec &in, PrepRec &out, float (&v)[16])
+                                            int &ps, const PrepRec &in, PrepRec &out, const Raw &rin, Raw &rout,
+                                            const Idx &xin, Idx &xout, float (&v)[16])
 {
     const int N = c.N;
-    unsigned char *slot = c.stage + c.lane * 32 + ps * 2048;
+    unsigned char *slot = c.stage + c.lane * 16 + ps * 2048;
     cpa_wait<kRingPairs - 1>();
-    prep_record<FIRST>(slot, out.gA, out.YA);                       // clamped at the end: harmless re-computation
-    prep_record<FIRST>(slot + 1024, out.gB, out.YB);
-    prep_load(c, slot, jj + 2 + 2 * kRingPairs, Lsrc, tbl, FIRST);
-    prep_load(c, slot + 1024, jj + 3 + 2 * kRingPairs, Lsrc, tbl, FIRST);
+#ifndef TPF_ABL_NORAW
+    raw_get<FIRST>(slot, rout);
+#else
+    rout = rin;
+#endif
+#ifndef TPF_ABL_NOCPA
+    Held held;
+    prep_load_pair(c, slot, jj + 4 + 2 * kRingPairs, Lsrc, xin, FIRST, held);
     cpa_commit();
+    if (!FIRST) idx_get(c, jj + 6 + 2 * kRingPairs, tbl, xout);
+#endif
     ps = ps == kRingPairs - 1 ? 0 : ps + 1;
+#ifndef TPF_ABL_NOFP64
+    prep_record(rin.xA, rin.laA, out.gA, out.YA);
+    prep_record(rin.xB, rin.laB, out.gB, out.YB);
+#else
+    out = in;
+#endif
     const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
+#ifndef TPF_ABL_NOREC
     if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
     else      smem_put(c, k0, in.gA);
+#endif
     // both steps' Y in one 256-bit store, ascending k (the beta lane walks k downwards: swap)
-    st256_f64(y_entry(c, c.isb ? k1 : k0), c.isb ? in.YB.x : in.YA.x, c.isb ? in.YB.y : in.YA.y,
-              c.isb ? in.YA.x : in.YB.x, c.isb ? in.YA.y : in.YB.y);
+    const double y0 = c.isb ? in.YB.x : in.YA.x, y1 = c.isb ? in.YB.y : in.YA.y;
+    const double y2 = c.isb ? in.YA.x : in.YB.x, y3 = c.isb ? in.YA.y : in.YB.y;
+    unsigned char *yp = y_entry(c, c.isb ? k1 : k0);
+#if !defined(TPF_ABL_NOY) && !defined(TPF_Y_LATE)
+    st256_f64(yp, y0, y1, y2, y3);
+#endif
     pass_step(v, in.gA, c.isb);
+#ifndef TPF_ABL_NOREC
     if (TMST) tm_st8(c.tq + 8u * (jj + 1), in.gB);
     else      smem_put(c, k1, in.gB);
+#endif
     pass_step(v, in.gB, c.isb);
+#if defined(TPF_Y_LATE)
+    st256_f64(yp, y0, y1, y2, y3);
+#endif
+#if !defined(TPF_ABL_NOCPA) && !defined(TPF_NOHOLD)
+    hold_until(c, v[15], held);
+#endif
+#if defined(TPF_Y_HOLD)
+    {
+        Held hy;
+        hy.r[0] = lo32(yp); hy.r[1] = __double2loint(y0); hy.r[2] = __double2hiint(y0);
+        hy.r[3] = __double2loint(y1); hy.r[4] = __double2hiint(y1); hy.r[5] = __double2loint(y2); hy.r[6] = __double2hiint(y2);
+        hold_until(c, v[15], hy);
+        Held hz;
+        hz.r[0] = hi32(yp); hz.r[1] = __double2loint(y3); hz.r[2] = __double2hiint(y3);
+        hz.r[3] = hz.r[4] = hz.r[5] = hz.r[6] = 0;
+        hold_until(c, v[14], hz);
+    }
+#endif
 }
 template <bool FIRST, bool TMST>
 __device__ __forceinline__ void pass1a_range(const Ctx &c, int j0, int j1, const float4 *Lsrc,
                                              const int16_t *tbl, PrepState &P, float (&v)[16])
 {
     PrepRec Q;
+    Raw RQ;
+    Idx XQ = P.ix;
     int jj = j0;
     for (; jj + 4 <= j1; jj += 4) {                                 // ping-pong: no register copies
-        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, v);
-        pass1a_pair<FIRST, TMST>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, v);
+        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
+        pass1a_pair<FIRST, TMST>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, RQ, P.raw, XQ, P.ix, v);
     }
     if (jj < j1) {
-        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, v);
+        pass1a_pair<FIRST, TMST>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
         P.r = Q;
+        P.raw = RQ;
+        P.ix = XQ;
     }
 }
 
@@ -428,21 +550,30 @@ __device__ __forceinline__ void pass1a(const Ctx &c, bool second, float (&v)[16]
 {
     const float4 *Lsrc = second ? c.L2A : c.L1A;
     const int16_t *tbl = second ? c.perm : c.inv;                   // La = Le[perm k] (:507-508) / Le[inv k] (:523-524)
-    unsigned char *ring = c.stage + c.lane * 32;
+    unsigned char *ring = c.stage + c.lane * 16;
+    PrepState P;
+    Held hd;
+    P.ix.a = P.ix.b = 0;
 #pragma unroll 1
     for (int p = 0; p < kRingPairs; ++p) {                          // ring of step pairs
-        prep_load(c, ring + p * 2048, 2 * p, Lsrc, tbl, FIRST);
-        prep_load(c, ring + p * 2048 + 1024, 2 * p + 1, Lsrc, tbl, FIRST);
+        if (!FIRST) idx_get(c, 2 * p, tbl, P.ix);
+        prep_load_pair(c, ring + p * 2048, 2 * p, Lsrc, P.ix, FIRST, hd);
         cpa_commit();
     }
-    PrepState P;
+    if (!FIRST) idx_get(c, 2 * kRingPairs, tbl, P.ix);
     cpa_wait<kRingPairs - 1>();
-    prep_record<FIRST>(ring, P.r.gA, P.r.YA);                        // steps 0, 1
-    prep_record<FIRST>(ring + 1024, P.r.gB, P.r.YB);
-    prep_load(c, ring, 2 * kRingPairs, Lsrc, tbl, FIRST);
-    prep_load(c, ring + 1024, 2 * kRingPairs + 1, Lsrc, tbl, FIRST);
+    raw_get<FIRST>(ring, P.raw);                                    // steps 0, 1
+    prep_record(P.raw.xA, P.raw.laA, P.r.gA, P.r.YA);
+    prep_record(P.raw.xB, P.raw.laB, P.r.gB, P.r.YB);
+    prep_load_pair(c, ring, 2 * kRingPairs, Lsrc, P.ix, FIRST, hd);
     cpa_commit();
-    P.ps = 1;
+    if (!FIRST) idx_get(c, 2 * kRingPairs + 2, tbl, P.ix);
+    cpa_wait<kRingPairs - 1>();
+    raw_get<FIRST>(ring + 2048, P.raw);                             // steps 2, 3
+    prep_load_pair(c, ring + 2048, 2 * kRingPairs + 2, Lsrc, P.ix, FIRST, hd);
+    cpa_commit();
+    if (!FIRST) idx_get(c, 2 * kRingPairs + 4, tbl, P.ix);
+    P.ps = 2 % kRingPairs;
     pass1a_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
     pass1a_range<FIRST, false>(c, c.T, c.M, Lsrc, tbl, P, v);
     cpa_wait<0>();
@@ -547,6 +678,7 @@ tpf_kernel(const TpfArgs A)
         __syncwarp();
     }
     c.perm = tab; c.inv = tab + N;
+    c.junk = 0;
     const int wg = blockIdx.x * kTpfWarps + warp;
     unsigned char *ws = A.ws + (size_t)wg * g.ws_per_warp;
     c.L1A = reinterpret_cast<float4 *>(ws + g.off_l1);
@@ -615,8 +747,8 @@ tpf_kernel(const TpfArgs A)
                             if (o2[i] >= 0) x2.z = row[o2[i]];
                             if (o3[i] >= 0) x2.w = row[o3[i]];
                         }
-                        __stcg(c.L1A + k * 16 + fr, x1);
-                        __stcg(c.L2A + k * 16 + fr, x2);
+                        st_ws(c.L1A + lpos(c, k, fr), x1);
+                        st_ws(c.L2A + lpos(c, k, fr), x2);
                     }
                 }
                 __syncwarp();
@@ -646,8 +778,8 @@ tpf_kernel(const TpfArgs A)
                 }
 #pragma unroll
                 for (int fr = 0; fr < 8; ++fr) {
-                    __stcg(c.L1A + k * 16 + f0 + fr, x1[fr]);
-                    __stcg(c.L2A + k * 16 + f0 + fr, x2[fr]);
+                    st_ws(c.L1A + lpos(c, k, f0 + fr), x1[fr]);
+                    st_ws(c.L2A + lpos(c, k, f0 + fr), x2[fr]);
                 }
             }
         }
@@ -671,7 +803,7 @@ tpf_kernel(const TpfArgs A)
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {                       // all loads of 8 couples in flight
                     const int k = min(w * 16 + t0 + t, N - 1);
-                    ab[t] = __ldcg(c.L1A + k * 16 + c.f);
+                    ab[t] = __ldcg(c.L1A + lpos(c, k, c.f));
                     la[t] = __ldcg(c.LeF + c.inv[k] * 16 + c.f);
                     e1[t] = __ldcg(c.Le + k * 16 + c.f);
                     rb[t] = make_uchar2(0, 0);
@@ -705,6 +837,7 @@ tpf_kernel(const TpfArgs A)
         __syncwarp();
         ph[6] += clock64() - t6;
     }
+    if (c.junk == 0x9e3779b9u && A.B < 0) g_tpf_cycles[0] = c.junk;   // never true: keeps the hold sink alive
     if (lane == 0) {
         ph[7] = clock64() - t_begin;
         for (int i = 0; i < 8; ++i) atomicAdd(&g_tpf_cycles[i], (unsigned long long)ph[i]);

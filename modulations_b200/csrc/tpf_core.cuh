@@ -136,8 +136,9 @@ TPF_HD void pass_step(float (&v)[16], const float (&g)[8], bool isb)
         n[2 * t + 1] = f_max(f_add(v[t], B), f_add(v[8 + t], A));
     }
     const float z = n[0];
+    v[0] = 0.f;                                       // fl(z - z): metrics are finite (the reference clips its inputs)
 #pragma unroll
-    for (int s = 0; s < 16; ++s) v[s] = f_sub(n[s], z);
+    for (int s = 1; s < 16; ++s) v[s] = f_sub(n[s], z);
 }
 
 // Backward step in natural labels: z = beta[k+1] -> beta[k] (dvb_rcs2_turbo.py:203-213).
@@ -153,8 +154,9 @@ TPF_HD void bwd_step(float (&z)[16], const float (&g)[8])
         n[8 + t] = f_max(f_add(z[2 * t], B), f_add(z[2 * t + 1], A));
     }
     const float q = n[0];
+    z[0] = 0.f;
 #pragma unroll
-    for (int s = 0; s < 16; ++s) z[s] = f_sub(n[s], q);
+    for (int s = 1; s < 16; ++s) z[s] = f_sub(n[s], q);
 }
 
 // Extrinsic maxima for step k (dvb_rcs2_turbo.py:239-248) fused with the forward step:
@@ -190,8 +192,9 @@ TPF_HD void ext_step(float (&x)[16], const float (&zs)[16], const float (&g)[8],
     }
     uv[0] = U0; uv[1] = U3; uv[2] = V1; uv[3] = V2;
     const float q = n[0];
+    x[0] = 0.f;
 #pragma unroll
-    for (int s = 0; s < 16; ++s) x[s] = f_sub(n[s], q);
+    for (int s = 1; s < 16; ++s) x[s] = f_sub(n[s], q);
 }
 
 // Extrinsic epilogue for one step (dvb_rcs2_turbo.py:250-279).

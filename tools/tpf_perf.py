@@ -35,7 +35,9 @@ for (N, rate, B) in cfgs:
           f"{fps*acs/1e12:.2f} TACS/s = {fps*acs/(64*148*1.965e9)*100:.1f}% of nominal ALU roofline; "
           f"BER={cnt[0]/cnt[3]:.4f} FER={cnt[1]/cnt[2]:.4f}")
     ph = np.zeros(8); lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
+    os.environ["B200DVB_TPF_TIMERS"] = "1"        # the instance of the kernel with per-phase clock64() accounting
     c.decode_batch(llr, ref_bits=info, counters=counters, out="none"); torch.cuda.synchronize()
+    del os.environ["B200DVB_TPF_TIMERS"]
     lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
     tot = ph[7]
     if tot > 0:

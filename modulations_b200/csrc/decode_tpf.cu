@@ -756,44 +756,73 @@ tpf_kernel(const TpfArgs A)
         const long long frame = frame0 + c.f;
         const bool live = frame < A.B;
         const int wpf = (2 * N + 31) / 32;
-        int any_err = 0;
-        for (int w = c.isb; w * 16 < N; w += 2) {
-            unsigned word = 0;
-#pragma unroll
-            for (int t0 = 0; t0 < 16; t0 += 8) {
-                float4 ab[8]; double2 la[8], e1[8]; uchar2 rb[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {                       // all loads of 8 couples in flight
-                    const int k = min(w * 16 + t0 + t, N - 1);
-                    ab[t] = __ldcg(c.L1A + lpos(c, k, c.f));
-                    la[t] = __ldcg(c.LeF + c.inv[k] * 16 + c.f);
-                    e1[t] = __ldcg(c.Le + k * 16 + c.f);
-                    rb[t] = make_uchar2(0, 0);
-                    if (live && A.ref_bits)
-                        rb[t] = *reinterpret_cast<const uchar2 *>(A.ref_bits + (size_t)frame * 2 * N + 2 * k);
-                }
+        // Batches of 8 couples per lane.  The phase is pure load latency and nothing else runs on this
+        // sub-partition meanwhile, so the three workspace streams (Lc, La = Le2[inv], Le1) of up to three batches
+        // ahead are kept in flight with cp.async into the record area, which is dead by now (registers cannot hold
+        // that much).  Batch b of a lane covers couples (isb + 2 (b >> 1)) * 16 + 8 (b & 1) + [0, 8); slots are
+        // lane-private, so no warp synchronisation is needed.
+        const bool cnt = live && A.ref_bits != nullptr;
+        const uint8_t *refp = cnt ? A.ref_bits + (size_t)frame * 2 * N : reinterpret_cast<const uint8_t *>(A.tab);
+        constexpr int kHB = 3 * 8 * 32 * 16;                        // bytes of one staged batch: [array][t][lane] x 16 B
+        const int rec_bytes_h = g.mid * 2 * 16 * (int)sizeof(float4);
+        unsigned char *hbuf = rec_bytes_h >= kHB ? reinterpret_cast<unsigned char *>(c.srec) : c.stage;
+        const int nst = rec_bytes_h >= 3 * kHB ? 3 : rec_bytes_h >= 2 * kHB ? 2 : 1;
+        const int nwords = (N + 15) / 16;                           // == wpf
+        const int nbu = 2 * ((nwords + 1) / 2);                     // batches of the alpha half (the beta half may idle through the last word)
+        auto hissue = [&](int b, int st) {
+            if (b < nbu) {
+                const int kb = (c.isb + 2 * (b >> 1)) * 16 + 8 * (b & 1);
+                const unsigned d = s_addr(hbuf + st * kHB + lane * 16) * c.one;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    const int k = w * 16 + t0 + t;
-                    if (k < N) {
-                        const double LA = d_add(d_add((double)ab[t].x, la[t].x), e1[t].x);
-                        const double LB = d_add(d_add((double)ab[t].y, la[t].y), e1[t].y);
-                        const int bA = LA < 0.0, bB = LB < 0.0;
-                        word |= (unsigned)(bA | (bB << 1)) << (2 * (t0 + t));
-                        if (live) {
-                            if (A.bits)
-                                *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * k) = make_int2(bA, bB);
-                            if (A.ref_bits) {
-                                const int errs = (bA != rb[t].x) + (bB != rb[t].y);
-                                bit_err += errs;
-                                any_err |= errs;
-                            }
-                        }
+                    const int k = min(kb + t, N - 1);
+                    const unsigned dt = d + t * 512;
+                    cpa16_off<0, 0>(dt, c.L1A + lpos(c, k, c.f));
+                    cpa16_off<4096, 0>(dt, c.LeF + c.inv[k] * 16 + c.f);
+                    cpa16_off<8192, 0>(dt, c.Le + k * 16 + c.f);
+                }
+            }
+            cpa_commit();
+        };
+        int any_err = 0;
+        unsigned word = 0;
+        for (int b = 0; b < nst; ++b) hissue(b, b);
+        for (int b = 0, st = 0; b < nbu; ++b) {
+            if (nst == 3) cpa_wait<2>(); else if (nst == 2) cpa_wait<1>(); else cpa_wait<0>();
+            const int kb = (c.isb + 2 * (b >> 1)) * 16 + 8 * (b & 1);
+            const unsigned char *src = hbuf + st * kHB + lane * 16;
+            unsigned short rb[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) rb[t] = *reinterpret_cast<const unsigned short *>(refp + 2 * min(kb + t, N - 1));
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int k = kb + t;
+                const float4 ab = *reinterpret_cast<const float4 *>(src + t * 512);
+                const double2 la = *reinterpret_cast<const double2 *>(src + 4096 + t * 512);
+                const double2 e1 = *reinterpret_cast<const double2 *>(src + 8192 + t * 512);
+                const double LA = d_add(d_add((double)ab.x, la.x), e1.x);
+                const double LB = d_add(d_add((double)ab.y, la.y), e1.y);
+                const int bA = LA < 0.0, bB = LB < 0.0;
+                if (k < N) {
+                    word |= (unsigned)(bA | (bB << 1)) << (2 * (8 * (b & 1) + t));
+                    if (live && A.bits)
+                        *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * k) = make_int2(bA, bB);
+                    if (cnt) {
+                        const int errs = (bA != (rb[t] & 0xff)) + (bB != (rb[t] >> 8));
+                        bit_err += errs;
+                        any_err |= errs;
                     }
                 }
             }
-            if (live && A.packed) A.packed[(size_t)frame * wpf + w] = word;
+            hissue(b + nst, st);                                    // refill the slot just read (same lane, same LSU queue: ordered)
+            st = st + 1 == nst ? 0 : st + 1;
+            if (b & 1) {
+                const int w = c.isb + b - 1;
+                if (live && A.packed && w < nwords) A.packed[(size_t)frame * wpf + w] = word;
+                word = 0;
+            }
         }
+        cpa_wait<0>();
         any_err |= __shfl_xor_sync(0xffffffffu, any_err, 16);
         if (live && !c.isb) { frames_done += 1; frm_err += any_err ? 1 : 0; }
         __syncwarp();

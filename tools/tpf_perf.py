@@ -27,16 +27,18 @@ for (N, rate, B) in cfgs:
     _lib.check(lib.b200dvb_mc_generate_bpsk(h.h, B, nv, 1234, 0, _lib.ptr(info), _lib.ptr(coded), _lib.ptr(llr), _lib.stream_ptr()), "mc")
     torch.cuda.synchronize()
     counters = torch.zeros(4, dtype=torch.int64, device="cuda")
-    best, avg = timeit(lambda: c.decode_batch(llr, ref_bits=info, counters=counters, out="none"))
+    ref = None if os.environ.get("NOREF") else info
+    outm = os.environ.get("OUT", "none")
+    best, avg = timeit(lambda: c.decode_batch(llr, ref_bits=ref, counters=counters, out=outm))
     cnt = counters.cpu().numpy()
     fps = B / (best * 1e-3)
     acs = 320 * N * 2 * 8
     print(f"N={N} B={B}: {best:.2f} ms (avg {avg:.2f})  {fps/1e6:.3f} Mframes/s  {fps*2*N/1e9:.3f} Gbit/s info  "
           f"{fps*acs/1e12:.2f} TACS/s = {fps*acs/(64*148*1.965e9)*100:.1f}% of nominal ALU roofline; "
-          f"BER={cnt[0]/cnt[3]:.4f} FER={cnt[1]/cnt[2]:.4f}")
+          f"BER={cnt[0]/max(cnt[3],1):.4f} FER={cnt[1]/max(cnt[2],1):.4f}")
     ph = np.zeros(8); lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
     os.environ["B200DVB_TPF_TIMERS"] = "1"        # the instance of the kernel with per-phase clock64() accounting
-    c.decode_batch(llr, ref_bits=info, counters=counters, out="none"); torch.cuda.synchronize()
+    c.decode_batch(llr, ref_bits=ref, counters=counters, out=outm); torch.cuda.synchronize()
     del os.environ["B200DVB_TPF_TIMERS"]
     lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
     tot = ph[7]

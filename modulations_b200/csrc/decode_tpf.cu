@@ -292,9 +292,20 @@ __device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int l
 // dependency stall except the instruction scheduler.
 // TM: the window's records are in TMEM — column block (wa + u) for the alpha lane, block
 // (wa + len-1-u) for the beta lane (the high records are stored in reverse).
+// the float64 epilogue of a window's LAST step, carried into the next window: there its dependent chain
+// (~50 instructions) fills the load latencies of the window start instead of running alone at the window end
+struct Pend { float uv[4], y[4]; int idx; };
+__device__ __forceinline__ void pend_flush(const Ctx &c, Pend &p, double sf, double2 *LeOut)
+{
+    double ea, eb;
+    make_extrinsic(p.uv, __hiloint2double(__float_as_int(p.y[1]), __float_as_int(p.y[0])),
+                   __hiloint2double(__float_as_int(p.y[3]), __float_as_int(p.y[2])), sf, ea, eb);
+    if (p.idx >= 0) st_ws(LeOut + p.idx * 16 + c.f, make_double2(ea, eb));
+    p.idx = -1;
+}
 template <bool TM>
 __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, double sf,
-                                       double2 *LeOut, int nslot, int nw0, int nlen)
+                                       double2 *LeOut, int nslot, int nw0, int nlen, Pend &pend)
 {
     Buf B;
     auto issue = [&](int u) {
@@ -314,6 +325,7 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         float Z[16];
         issue(len - 1);
         slot_get(c.slotZ(), c.lane, Z);
+        pend_flush(c, pend, sf, LeOut);                             // previous window's last step
         complete(g);
         for (int u = len - 1; u >= 0; --u) {
             slot_put(ws + u * 128, 0, Z);                           // beta[k+1]
@@ -349,12 +361,9 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
 #pragma unroll
         for (int i = 0; i < 4; ++i) { uvp[i] = uv[i]; yr[i] = yn[i]; }
     }
-    {
-        double ea, eb;
-        make_extrinsic(uvp, __hiloint2double(__float_as_int(yr[1]), __float_as_int(yr[0])),
-                       __hiloint2double(__float_as_int(yr[3]), __float_as_int(yr[2])), sf, ea, eb);
-        st_ws(LeOut + (w0 + len - 1) * 16 + c.f, make_double2(ea, eb));
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pend.uv[i] = uvp[i]; pend.y[i] = yr[i]; }
+    pend.idx = w0 + len - 1;
     if (c.isb) slot_put(c.slotX(), c.lane, X);                      // running alpha of the beta lane
     if (nlen) yq_park(c, nq, nw0, nlen, nslot - 1);
 }
@@ -573,16 +582,21 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     issue_ckpt(c, 0);
     cpa_commit();
     // ---- out phase: windows from the crossing point outwards ---------------------------------
+    Pend pend;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pend.uv[i] = pend.y[i] = 0.f;
+    pend.idx = -1;
     for (int i = 0; i < nwin; ++i) {
         cpa_wait<0>();
         __syncwarp();
         const int wa = i < nfull ? M - (i + 1) * kW : 0;
         const int nlen = i + 1 < nwin ? win_len(i + 1) : 0;
         const int nw0 = i + 1 < nwin ? win_w0(i + 1) : 0;
-        if (i < n_inner) window<false>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen);
-        else             window<true>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen);
+        if (i < n_inner) window<false>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
+        else             window<true>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
         if (TIMED && i == n_inner - 1) { const long long t = clock64(); ph[4] += t - tA; tA = t; }
     }
+    pend_flush(c, pend, sf, LeOut);
     cpa_wait<0>();
     __syncwarp();
     if (TIMED) { const long long t = clock64(); ph[5] += t - tA; tA = t; }

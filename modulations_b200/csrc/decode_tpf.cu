@@ -195,7 +195,9 @@ __device__ __forceinline__ void run_pass(const Ctx &c, int j0, int j1, float (&v
     float g[8];
     pf_issue<KIND>(c, j0, B0);
     pf_complete<KIND>(c, B0, g);
-    for (int j = j0; j < j1; j += 2) {
+    // steps j, j+1 with the record of step j in g; leaves the record of step j+2 in g.  Loads past the end are
+    // clamped (a harmless re-read), so the body is branch-free apart from the checkpoint store.
+    auto two = [&](int j) {
         pf_issue<KIND>(c, j + 1, B1);
         if (CKPT) {
             if (((c.M - j) % kW) == 0) ck_store(c, (c.M - j) / kW - 1, v);
@@ -203,10 +205,13 @@ __device__ __forceinline__ void run_pass(const Ctx &c, int j0, int j1, float (&v
         }
         pass_step(v, g, c.isb);
         pf_complete<KIND>(c, B1, g);
-        if (j + 2 < j1) pf_issue<KIND>(c, j + 2, B0);
+        pf_issue<KIND>(c, min(j + 2, j1 - 1), B0);
         pass_step(v, g, c.isb);
-        if (j + 2 < j1) pf_complete<KIND>(c, B0, g);
-    }
+        pf_complete<KIND>(c, B0, g);
+    };
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) { two(j); two(j + 2); }             // four steps per iteration: loop overhead and the
+    if (j < j1) two(j);                                             // instruction-fetch bubble of the back edge amortised
 }
 
 __device__ __forceinline__ void issue_ckpt(const Ctx &c, int slot)

@@ -330,9 +330,15 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
         float Z[16];
         issue(len - 1);
         slot_get(c.slotZ(), c.lane, Z);
-        pend_flush(c, pend, sf, LeOut);                             // previous window's last step
         complete(g);
-        for (int u = len - 1; u >= 0; --u) {
+        // first step of the way down peeled (len >= 2): the float64 epilogue chain of the previous window's last
+        // step shares its basic block, so the scheduler interleaves the chain with the step's 64 independent FP32 ops
+        slot_put(ws + (len - 1) * 128, 0, Z);
+        issue(len - 2);
+        pend_flush(c, pend, sf, LeOut);
+        bwd_step(Z, g);
+        complete(g);
+        for (int u = len - 2; u >= 0; --u) {
             slot_put(ws + u * 128, 0, Z);                           // beta[k+1]
             issue(u > 0 ? u - 1 : 0);                               // u == 0: first record of the way up
             bwd_step(Z, g);

@@ -32,6 +32,9 @@ NOMINAL_ACS_PER_CLK_SM = 64.0                        # 1 FADD + 1 FMNMX per ACS 
 METRIC = "turbo_info_throughput_N212_R1/3_8it"
 
 
+_OUT = sys.stdout
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -133,7 +136,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -214,16 +217,16 @@ def run_ours(args, rank, world, local_rank):
         pass
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 108 693 B/frame at 65 536 "
+            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 105 129 B/frame at 65 536 "
                             "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
                             "reference bits in). The rest is decoder scratch that does not fit the 126 MB L2 with 64 "
                             "frames per SM in flight: the transposed channel LLRs are re-read every half-iteration "
                             "(3 392 B x 16) and the extrinsics are written back between half-iterations; dead scratch "
-                            "lines are dropped with discard.global.L2 (was 237 KB/frame without). 12 % of HBM peak.",
+                            "lines are dropped with discard.global.L2 (was 237 KB/frame without). 11 % of HBM peak.",
             "note": "ACS = add-compare-select of the reference algorithm (320*N per SISO, SURVEY 8d); peak = "
                     "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at "
                     "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). The kernel is bound by "
-                    "instruction issue (ncu: 55 % issue-active with one warp per scheduler), not by HBM (12 % of the "
+                    "instruction issue (ncu: 61 % issue-active with one warp per scheduler), not by HBM (11 % of the "
                     "copy peak), so MEASURED_PEAKS.json has no denominator for it.",
             "frac_at_measured_clock": (achieved / (NOMINAL_ACS_PER_CLK_SM * sms * clocks["sm_mhz"] * 1e6 / 1e12))
             if clocks.get("sm_mhz") else None}
@@ -337,7 +340,7 @@ def run_ours(args, rank, world, local_rank):
             "microbench_lane_ops_per_clk_sm": {k: float(v) for k, v in zip(
                 ("fadd", "fmnmx", "acs_mix", "shfl", "dadd", "f2f", "fadd_x2", "clock_mhz"), mb)},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -361,6 +364,13 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    # stdout carries ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL prints
+    # "NCCL version ..." there on some boxes): fd 1 is pointed at stderr for the whole run and the line goes to a
+    # private duplicate of the original stdout.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -24,9 +24,9 @@
 //     the same TMEM lane.
 //   * prep (gather, a-priori add, float64 branch sums) is fused into the first half of pass
 //     1: the alpha lane builds records 0.., the beta lane N-1.. exactly when it needs them.
-//   * meet in the middle (M = N/2) with a checkpoint every 8 steps; after the crossing the
-//     half-warps swap chains through a shuffle: the alpha lane walks beta down over [0, M),
-//     the beta lane walks alpha up over [M, N), each re-computing the other direction 8
+//   * meet in the middle (M = N/2) with a checkpoint every 4 steps; after the crossing the
+//     half-warps swap chains through their staging slots: the alpha lane walks beta down over
+//     [0, M), the beta lane walks alpha up over [M, N), each re-computing the other direction 4
 //     steps at a time from its OWN checkpoints (same operations, same order: exact).  The
 //     extrinsic epilogue (float64) is fused into that walk; a-priori / extrinsic values live
 //     in an L2-resident workspace laid out [step][frame] so every access is coalesced.
@@ -390,9 +390,8 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
 __device__ __forceinline__ int lpos(const Ctx &c, int k, int fr) { return k < c.M ? k * 32 + fr : (c.N - 1 - k) * 32 + 16 + fr; }
 
 // cp.async with immediate offsets on both addresses: the four copies of a step pair share ONE destination
-// register (and the two channel copies one source register).  A register that a cp.async reads stays busy
-// for ~20 cycles after issue; ptxas re-used the per-copy address temporaries at once and the lone warp of
-// the sub-partition sat in a write-after-read stall after every copy (profiles/r01_tpf_stalls.txt).
+// register (and the two channel copies one source register): a handful of address instructions per pair instead
+// of a multiply + LEA pair per copy.
 template <int DOFF, int SOFF>
 __device__ __forceinline__ void cpa16_off(unsigned d, const void *src)
 {
@@ -427,8 +426,10 @@ __device__ __forceinline__ void prep_load_pair(const Ctx &c, unsigned char *slot
         cpa16_off<1536, 0>(d, c.Le + x.b * 16 + c.f);
     }
 }
-// raw inputs of a step pair, read out of the ring a whole pair before they are needed: the shared-memory
-// load that follows a cp.async wait is ~60 cycles away for a warp with nothing else to run
+// raw inputs of a step pair, read out of the ring a whole pair before they are needed: a shared-memory load
+// queued behind the ring traffic can take several times its nominal 29 cycles to return, and this warp has
+// nothing else to run meanwhile.  Ring slot of a pair: [x A][la A][x B][la B], 512 B each, lane-major: both the
+// cp.async writes and these LDS.128 are bank-conflict free (a [lane][x|la] slot cost 32 smem wavefronts per copy)
 struct Raw { float4 xA, xB; double2 laA, laB; };
 template <bool FIRST>
 __device__ __forceinline__ void raw_get(const unsigned char *slot, Raw &r)
@@ -450,6 +451,7 @@ struct PrepRec { float gA[8], gB[8]; double2 YA, YB; };      // records and Lc+L
 struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; };
 // steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 (raw inputs `rin`) into
 // `out` and pulls the raw inputs of steps jj+4, jj+5 out of the ring into `rout`
+// (TPF_ABL_* : timing-only ablation builds for profiles/r01_tpf_ablation.txt; never defined in the shipped library)
 template <bool FIRST, bool TMST>
 __device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *Lsrc, const int16_t *tbl,
                                             int &ps, const PrepRec &in, PrepRec &out, const Raw &rin, Raw &rout,

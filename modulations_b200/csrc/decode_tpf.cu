@@ -442,12 +442,22 @@ __device__ __forceinline__ void raw_get(const unsigned char *slot, Raw &r)
         r.laB = *reinterpret_cast<const double2 *>(slot + 1536);
     }
 }
-__device__ __forceinline__ void prep_record(const float4 &x, const double2 &la, float (&g)[8], double2 &Y)
+// records of the step pair (jn, jn+1) from its raw inputs; Y = Lc + La of both steps goes to the workspace at once
+// (one 256-bit store, ascending k: the beta lane walks k downwards, so its two steps swap) instead of riding along
+// in registers until the pair is stepped
+struct PrepRec { float gA[8], gB[8]; };                      // records of two consecutive steps
+__device__ __forceinline__ void prep_pair(const Ctx &c, const Raw &r, int jn, PrepRec &out)
 {
-    Y = make_double2(d_add((double)x.x, la.x), d_add((double)x.y, la.y));    // Lc + La (:135)
-    make_record(Y.x, Y.y, x.z, x.w, g);
+    jn = min(jn, c.M - 2);
+    const double2 YA = make_double2(d_add((double)r.xA.x, r.laA.x), d_add((double)r.xA.y, r.laA.y));    // Lc + La (:135)
+    const double2 YB = make_double2(d_add((double)r.xB.x, r.laB.x), d_add((double)r.xB.y, r.laB.y));
+    make_record(YA.x, YA.y, r.xA.z, r.xA.w, out.gA);
+    make_record(YB.x, YB.y, r.xB.z, r.xB.w, out.gB);
+#ifndef TPF_ABL_NOY
+    const int ke = c.isb ? c.N - 2 - jn : jn;                       // the even (lower) k of the pair
+    st256_f64(y_entry(c, ke), c.isb ? YB.x : YA.x, c.isb ? YB.y : YA.y, c.isb ? YA.x : YB.x, c.isb ? YA.y : YB.y);
+#endif
 }
-struct PrepRec { float gA[8], gB[8]; double2 YA, YB; };      // records and Lc+La of two consecutive steps
 struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; };
 // steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 (raw inputs `rin`) into
 // `out` and pulls the raw inputs of steps jj+4, jj+5 out of the ring into `rout`
@@ -472,8 +482,7 @@ __device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *
 #endif
     ps = ps == kRingPairs - 1 ? 0 : ps + 1;
 #ifndef TPF_ABL_NOFP64
-    prep_record(rin.xA, rin.laA, out.gA, out.YA);
-    prep_record(rin.xB, rin.laB, out.gB, out.YB);
+    prep_pair(c, rin, jj + 2, out);
 #else
     out = in;
 #endif
@@ -481,13 +490,6 @@ __device__ __forceinline__ void pass1a_pair(const Ctx &c, int jj, const float4 *
 #ifndef TPF_ABL_NOREC
     if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
     else      smem_put(c, k0, in.gA);
-#endif
-    // both steps' Y in one 256-bit store, ascending k (the beta lane walks k downwards: swap)
-    const double y0 = c.isb ? in.YB.x : in.YA.x, y1 = c.isb ? in.YB.y : in.YA.y;
-    const double y2 = c.isb ? in.YA.x : in.YB.x, y3 = c.isb ? in.YA.y : in.YB.y;
-    unsigned char *yp = y_entry(c, c.isb ? k1 : k0);
-#ifndef TPF_ABL_NOY
-    st256_f64(yp, y0, y1, y2, y3);
 #endif
     pass_step(v, in.gA, c.isb);
 #ifndef TPF_ABL_NOREC
@@ -533,8 +535,7 @@ __device__ __forceinline__ void pass1a(const Ctx &c, bool second, float (&v)[16]
     if (!FIRST) idx_get(c, 2 * kRingPairs, tbl, P.ix);
     cpa_wait<kRingPairs - 1>();
     raw_get<FIRST>(ring, P.raw);                                    // steps 0, 1
-    prep_record(P.raw.xA, P.raw.laA, P.r.gA, P.r.YA);
-    prep_record(P.raw.xB, P.raw.laB, P.r.gB, P.r.YB);
+    prep_pair(c, P.raw, 0, P.r);
     prep_load_pair(c, ring, 2 * kRingPairs, Lsrc, P.ix, FIRST);
     cpa_commit();
     if (!FIRST) idx_get(c, 2 * kRingPairs + 2, tbl, P.ix);

@@ -962,6 +962,12 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     // whole rows by 16-byte cp.async: pitch and base 16-byte aligned, row fits half the staging area
     A.vec4 = (c.N <= 256) && (llr_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && ((c.n_llr + 3) / 4 * 4 <= kRowFloats) &&
              !getenv("B200DVB_NOVEC4");
+    if (A.vec4) {   // the group-staged transposition needs at least two padded rows (+ the offset table) in one of the warp's areas
+        const int nq = (c.n_llr + 3) / 4, pitch4 = ((nq + 6) & ~7) + 1;
+        const int rec_bytes = c.tpf.mid * 2 * 16 * (int)sizeof(float4);
+        const int avail = rec_bytes > kStageBytes ? rec_bytes : kStageBytes - c.N * 16;
+        if (avail / (pitch4 * 16) < 2) A.vec4 = 0;
+    }
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;

@@ -217,7 +217,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 105 129 B/frame at 65 536 "
+            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 106 200 B/frame at 65 536 "
                             "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
                             "reference bits in). The rest is decoder scratch that does not fit the 126 MB L2 with 64 "
                             "frames per SM in flight: the transposed channel LLRs are re-read every half-iteration "
@@ -226,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
             "note": "ACS = add-compare-select of the reference algorithm (320*N per SISO, SURVEY 8d); peak = "
                     "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at "
                     "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). The kernel is bound by "
-                    "instruction issue (ncu: 61 % issue-active with one warp per scheduler), not by HBM (11 % of the "
+                    "instruction issue (ncu: 60 % issue-active with one warp per scheduler), not by HBM (11 % of the "
                     "copy peak), so MEASURED_PEAKS.json has no denominator for it.",
             "frac_at_measured_clock": (achieved / (NOMINAL_ACS_PER_CLK_SM * sms * clocks["sm_mhz"] * 1e6 / 1e12))
             if clocks.get("sm_mhz") else None}

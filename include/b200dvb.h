@@ -165,7 +165,9 @@ int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
 int b200dvb_debug_phase_cycles(double *out8_h, int reset);
 /* Same for the thread-per-frame kernel (summed over warps): {transpose-in, pass 1 first half
  * incl. prep, pass 1 second half, pass 2 to the crossing, out-phase windows in shared memory,
- * out-phase windows in tensor memory, hard decision, warp total}. */
+ * out-phase windows in tensor memory, hard decision, warp total}.  Only launches made while the
+ * environment variable B200DVB_TPF_TIMERS is set run the instance of the kernel that keeps these
+ * counters (the production instance has no clock reads); tools/tpf_perf.py shows the use. */
 int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the

@@ -252,7 +252,12 @@ def run_ours(args, rank, world, local_rank):
         demap[name] = {"gsym_per_s": nsym / (np.mean(ts) * 1e-3) / 1e9, "achieved_gbs": gbs,
                        "peak_gbs": mp.get("hbm_gbs", 6650.0), "frac": gbs / mp.get("hbm_gbs", 6650.0),
                        "peak_source": "measured" if "hbm_gbs" in mp else "fallback",
-                       "bytes_per_symbol": 8 + 4 * m.bps, "symbols": nsym}
+                       "bytes_per_symbol": 8 + 4 * m.bps, "symbols": nsym,
+                       # the same figures in the roofline object's vocabulary (HBM-bound kernel); traffic = DRAM bytes of
+                       # one launch from the committed ncu capture (profiles/r01_demap_ncu.txt: 16QAM, 2^27 symbols)
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": mp.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                                    "frac": gbs / mp.get("hbm_gbs", 6650.0),
+                                    "traffic": (1.073748e9 + 2.094105e9) * nsym / (1 << 27) if name == "16QAM" else None}}
         del out
     del iq
 

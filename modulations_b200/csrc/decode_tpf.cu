@@ -187,31 +187,46 @@ __device__ __forceinline__ void ck_store(const Ctx &c, int slot, const float (&v
 
 // steps [j0, j1) of an "in" pass (j1 - j0 even), records of storage class KIND; CKPT: store a
 // checkpoint wherever (M - j) is a multiple of kW (pass 2 only; those j are even)
+// steps j, j+1 of an "in" pass with the record of step j in g; leaves the record of step j+2 in g.  Loads past the
+// end are clamped (a harmless re-read).  CK: a checkpoint is due before step j — a compile-time fact, so that the
+// body stays ONE basic block (a branch around the store keeps the scheduler from interleaving across it)
+template <int KIND, bool CK>
+__device__ __forceinline__ void pass_two(const Ctx &c, int j, int j1, Buf &B0, Buf &B1, float (&g)[8], float (&v)[16])
+{
+    pf_issue<KIND>(c, j + 1, B1);
+    if (CK) ck_store(c, (c.M - j) / kW - 1, v);
+    pass_step(v, g, c.isb);
+    pf_complete<KIND>(c, B1, g);
+    pf_issue<KIND>(c, min(j + 2, j1 - 1), B0);
+    pass_step(v, g, c.isb);
+    pf_complete<KIND>(c, B0, g);
+}
+template <int KIND, bool CKA, bool CKB>
+__device__ __forceinline__ void pass_loop(const Ctx &c, int j0, int j1, Buf &B0, Buf &B1, float (&g)[8], float (&v)[16])
+{
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {                                   // four steps per iteration: loop overhead and the
+        pass_two<KIND, CKA>(c, j, j1, B0, B1, g, v);                // instruction-fetch bubble of the back edge amortised
+        pass_two<KIND, CKB>(c, j + 2, j1, B0, B1, g, v);
+    }
+    if (j < j1) pass_two<KIND, CKA>(c, j, j1, B0, B1, g, v);
+}
+// steps [j0, j1) of an "in" pass (j1 - j0 even), records of storage class KIND; CKPT (pass 2 only): a checkpoint
+// wherever (M - j) is a multiple of kW = 4 — every second step pair, starting with the first pair of the range or
+// with the second — plus the one of the ragged last window at j = 0
 template <int KIND, bool CKPT>
 __device__ __forceinline__ void run_pass(const Ctx &c, int j0, int j1, float (&v)[16])
 {
+    static_assert(kW == 4, "checkpoints alternate between the step pairs of a four-step body");
     if (j0 >= j1) return;
     Buf B0, B1;
     float g[8];
     pf_issue<KIND>(c, j0, B0);
     pf_complete<KIND>(c, B0, g);
-    // steps j, j+1 with the record of step j in g; leaves the record of step j+2 in g.  Loads past the end are
-    // clamped (a harmless re-read), so the body is branch-free apart from the checkpoint store.
-    auto two = [&](int j) {
-        pf_issue<KIND>(c, j + 1, B1);
-        if (CKPT) {
-            if (((c.M - j) % kW) == 0) ck_store(c, (c.M - j) / kW - 1, v);
-            else if (j == 0) ck_store(c, c.M / kW, v);
-        }
-        pass_step(v, g, c.isb);
-        pf_complete<KIND>(c, B1, g);
-        pf_issue<KIND>(c, min(j + 2, j1 - 1), B0);
-        pass_step(v, g, c.isb);
-        pf_complete<KIND>(c, B0, g);
-    };
-    int j = j0;
-    for (; j + 4 <= j1; j += 4) { two(j); two(j + 2); }             // four steps per iteration: loop overhead and the
-    if (j < j1) two(j);                                             // instruction-fetch bubble of the back edge amortised
+    if (!CKPT) { pass_loop<KIND, false, false>(c, j0, j1, B0, B1, g, v); return; }
+    if (j0 == 0 && (c.M % kW) != 0) ck_store(c, c.M / kW, v);
+    if (((c.M - j0) % kW) == 0) pass_loop<KIND, CKPT, false>(c, j0, j1, B0, B1, g, v);
+    else                        pass_loop<KIND, false, CKPT>(c, j0, j1, B0, B1, g, v);
 }
 
 __device__ __forceinline__ void issue_ckpt(const Ctx &c, int slot)

@@ -369,8 +369,8 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, do
     tm_ld4(c.tq + c.ycol, yr);
     issue(len > 1 ? 1 : 0);
     slot_get(ws, 0, zs);
+    ext_step(X, zs, g, uvp);                                        // step 0 (its Y is not needed before the next step's epilogue)
     tm_wait_ld4(yr);
-    ext_step(X, zs, g, uvp);                                        // step 0
     complete(g);
     for (int u = 1; u < len; ++u) {
         tm_ld4(c.tq + c.ycol + 4u * u, yn);

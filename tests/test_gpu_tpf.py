@@ -107,3 +107,25 @@ def test_host_pipeline_matches_resident_decode(chunk):
     assert bool((out.cuda() == want).all())
     ref = torch.from_numpy(o.decode_batch(llr))
     assert bool((out[:16] == ref).all())
+
+
+def test_timed_kernel_instance_is_bit_exact_too(monkeypatch):
+    """B200DVB_TPF_TIMERS selects the template instance with per-phase clock64() accounting
+    (tools/tpf_perf.py); it must decode exactly like the production instance and fill the counters."""
+    from modulations_b200 import _lib
+    N, rate, iters, nfr = 212, '1/3', 2, 33
+    o = oracle.OracleTurbo(N, rate, iters)
+    info, llr = _llrs(o, N, rate, nfr, 2.0, 777)
+    ref = o.decode_batch(llr)
+    g = _codec(N, rate, iters, "tpf")
+    lib = _lib.load()
+    ph = np.zeros(8)
+    _lib.check(lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1), "reset")
+    assert np.array_equal(g.decode_batch(llr), ref)
+    _lib.check(lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1), "read")
+    assert ph[7] == 0, "the production instance keeps no phase counters"
+    monkeypatch.setenv("B200DVB_TPF_TIMERS", "1")
+    assert np.array_equal(g.decode_batch(llr), ref)
+    monkeypatch.delenv("B200DVB_TPF_TIMERS")
+    _lib.check(lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1), "read")
+    assert ph[7] > 0 and abs(ph[:7].sum() - ph[7]) <= 0.05 * ph[7]

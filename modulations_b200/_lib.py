@@ -44,6 +44,8 @@ SIGNATURES = {
     "b200dvb_map": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "b200dvb_demap": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_float, _c_float, _c_void_p, _c_void_p]),
     "b200dvb_hard_demod": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_int, _c_void_p, _c_void_p]),
+    "b200dvb_pulse_shape": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "b200dvb_matched_filter": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_size_t, _c_void_p, _c_void_p]),
     "b200dvb_debug_phase_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_debug_tpf_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_tmem_selftest": (_c_int, [_c_void_p]),

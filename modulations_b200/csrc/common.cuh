@@ -123,6 +123,10 @@ int launch_demap(const Modem &m, size_t n, const void *iq, float noise_var, floa
                  float *llr, cudaStream_t s);
 int launch_hard(const Modem &m, size_t n, const void *iq, int in_f64, uint8_t *bits, cudaStream_t s);
 
+int launch_pulse_shape(size_t n_sym, const void *sym, const float *taps, int ntaps, int sps, void *out, cudaStream_t s);
+int launch_matched_filter(size_t n, const void *x, const float *taps, int ntaps, int sps, long long start,
+                          size_t n_out, void *out, cudaStream_t s);
+
 int modem_build_pwl(Modem &m);
 int run_microbench(double *results_h);
 int run_tmem_selftest(int *result_h);

@@ -1,13 +1,37 @@
-"""Drop-in for the mapping half of the reference ``modulators.Modulator``
-(``modulators.py:119-200``): natural-binary (non-Gray) BPSK/QPSK/8PSK/16/64QAM.
-Same kernels as ``SDRModem``, different constellation tables.  Pulse shaping
-(``modulators.py:19-115``) is out of scope.
+"""Drop-in for the reference ``modulators.Modulator``: the natural-binary (non-Gray)
+BPSK/QPSK/8PSK/16/64QAM mapping (``modulators.py:119-200`` — same kernels as ``SDRModem``,
+different constellation tables) and the waveform stage next to it (``modulators.py:19-117``:
+``rrcosfilter``, ``apply_pulse_shaping``, ``matched_filter`` — SURVEY 8(f) N4), as streaming
+FIR kernels behind ``b200dvb_pulse_shape`` / ``b200dvb_matched_filter``.
 """
 from __future__ import annotations
 
 import numpy as np
 
+from . import _lib
 from .sdr_modem import ModemHandle
+
+
+def rrcosfilter(N, alpha, Ts, Fs):
+    """Root-raised-cosine taps with unit energy (``modulators.py:19-48``): ``int(N*Fs) | 1`` taps,
+    the singular points t = 0 and abs(t) = Ts/(4 alpha) in closed form, denominator clamped at 1e-10.
+    Host-side table generation (49 numbers); the FIRs that use the table run on the GPU."""
+    num_taps = int(N * Fs) | 1
+    t = (np.arange(num_taps) - (num_taps - 1) / 2) * (1.0 / float(Fs))
+    h = np.zeros(num_taps, dtype=float)
+    for i, tt in enumerate(t):
+        if tt == 0.0:
+            h[i] = 1.0 - alpha + (4 * alpha / np.pi)
+        elif alpha != 0 and abs(tt) == Ts / (4 * alpha):
+            h[i] = (alpha / np.sqrt(2)) * (((1 + 2 / np.pi) * (np.sin(np.pi / (4 * alpha))))
+                                           + ((1 - 2 / np.pi) * (np.cos(np.pi / (4 * alpha)))))
+        else:
+            denom = (1 - (4 * alpha * tt / Ts) ** 2)
+            if abs(denom) < 1e-10:
+                denom = 1e-10
+            num = np.sin(np.pi * tt / Ts * (1 - alpha)) + 4 * alpha * tt / Ts * np.cos(np.pi * tt / Ts * (1 + alpha))
+            h[i] = num / (np.pi * tt / Ts * denom)
+    return h / np.sqrt(np.sum(h ** 2))
 
 
 def natural_constellation(modulation):
@@ -29,9 +53,54 @@ def natural_constellation(modulation):
 
 
 class Modulator:
-    def __init__(self, sps=4, alpha=0.35, span=6):
-        self.sps, self.alpha, self.span = sps, alpha, span
+    def __init__(self, samples_per_symbol=8, bt=0.3, rrc_alpha=0.35, rrc_span=6):
+        """Same arguments and attributes as the reference constructor (``modulators.py:52-63``)."""
+        self.sps = int(samples_per_symbol)
+        self.bt = float(bt)
+        self.rrc_alpha = rrc_alpha
+        self.rrc_span = rrc_span
+        self.rrc_filter = rrcosfilter(self.rrc_span, self.rrc_alpha, 1, self.sps)
+        self.filter_delay = (len(self.rrc_filter) - 1) // 2
         self._h = {}
+        self._taps_dev = None
+
+    # ============ PULSE SHAPING (modulators.py:85-117) ============
+    def _taps(self):
+        if self._taps_dev is None:
+            torch = _lib.require_cuda()
+            self._taps_dev = _lib.to_device(self.rrc_filter.astype(np.float32), torch.float32)
+        return self._taps_dev
+
+    def apply_pulse_shaping(self, symbols):
+        """Upsample by ``sps`` and apply the TX RRC filter: ``upfirdn(rrc_filter, complex64(symbols), up=sps)``
+        (``:85-100``), length ``(n-1)*sps + len(rrc_filter)``.  numpy in -> complex128 numpy out (the
+        reference's dtype; the values carry float32 accuracy), CUDA tensor in -> complex64 CUDA tensor out."""
+        torch = _lib.require_cuda()
+        is_torch = isinstance(symbols, torch.Tensor)
+        s = _lib.to_device(symbols if is_torch else np.asarray(symbols).astype(np.complex64), torch.complex64).reshape(-1)
+        n, nt = s.numel(), len(self.rrc_filter)
+        out = torch.empty((n - 1) * self.sps + nt if n else 0, dtype=torch.complex64, device=s.device)
+        if n:
+            _lib.check(_lib.load().b200dvb_pulse_shape(n, _lib.ptr(s), _lib.ptr(self._taps()), nt, self.sps,
+                                                       _lib.ptr(out), _lib.stream_ptr()), "pulse_shape")
+        return out if is_torch else out.cpu().numpy().astype(np.complex128)
+
+    def matched_filter(self, samples):
+        """RX RRC filter and symbol-rate decimation: ``convolve(samples, rrc_filter, 'full')[2*filter_delay::sps]``
+        (``:102-117``); an empty complex64 array when the start index is past the end, as the reference returns."""
+        torch = _lib.require_cuda()
+        is_torch = isinstance(samples, torch.Tensor)
+        x = _lib.to_device(samples if is_torch else np.asarray(samples).astype(np.complex64), torch.complex64).reshape(-1)
+        n, nt = x.numel(), len(self.rrc_filter)
+        start = 2 * self.filter_delay
+        full = n + nt - 1 if n else 0
+        if start >= full:
+            return torch.empty(0, dtype=torch.complex64, device=x.device) if is_torch else np.array([], dtype=np.complex64)
+        n_out = (full - start + self.sps - 1) // self.sps
+        out = torch.empty(n_out, dtype=torch.complex64, device=x.device)
+        _lib.check(_lib.load().b200dvb_matched_filter(n, _lib.ptr(x), _lib.ptr(self._taps()), nt, self.sps, start,
+                                                      n_out, _lib.ptr(out), _lib.stream_ptr()), "matched_filter")
+        return out if is_torch else out.cpu().numpy().astype(np.complex128)
 
     def _modem(self, name):
         if name not in self._h:

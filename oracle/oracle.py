@@ -385,3 +385,50 @@ def compute_llr(syms, mod_type, noise_var, constellation=None, chunk=1 << 16):
         for b, (i0, i1) in enumerate(sets):
             out[lo:lo + chunk, b] = (d[:, i0].min(axis=1) - d[:, i1].min(axis=1)) / noise_var
     return np.clip(out.reshape(-1), -30, 30)
+
+
+# =============================================================================
+# Waveform stage — modulators.py:19-117 (rrcosfilter, apply_pulse_shaping, matched_filter)
+# =============================================================================
+def rrcosfilter(N, alpha, Ts, Fs):
+    """Root-raised-cosine taps, unit energy (modulators.py:19-48): odd tap count int(N*Fs)|1, the two
+    singular points handled as the reference does, denominator clamped at 1e-10."""
+    num_taps = int(N * Fs) | 1
+    t = (np.arange(num_taps) - (num_taps - 1) / 2) * (1.0 / float(Fs))
+    h = np.zeros(num_taps, dtype=float)
+    for x in range(num_taps):
+        tt = t[x]
+        if tt == 0.0:
+            h[x] = 1.0 - alpha + (4 * alpha / np.pi)
+        elif alpha != 0 and abs(tt) == Ts / (4 * alpha):
+            h[x] = (alpha / np.sqrt(2)) * (((1 + 2 / np.pi) * (np.sin(np.pi / (4 * alpha))))
+                                           + ((1 - 2 / np.pi) * (np.cos(np.pi / (4 * alpha)))))
+        else:
+            denom = (1 - (4 * alpha * tt / Ts) ** 2)
+            if abs(denom) < 1e-10:
+                denom = 1e-10
+            num = (np.sin(np.pi * tt / Ts * (1 - alpha)) + 4 * alpha * tt / Ts * np.cos(np.pi * tt / Ts * (1 + alpha)))
+            h[x] = num / (np.pi * tt / Ts * denom)
+    return h / np.sqrt(np.sum(h ** 2))
+
+
+def pulse_shape(symbols, h, sps):
+    """apply_pulse_shaping (modulators.py:85-100) = scipy.signal.upfirdn(h, syms, up=sps, down=1):
+    zero-stuff by sps, convolve 'full', keep (n-1)*sps + len(h) samples.  complex64 in, complex128 out."""
+    syms = np.array(symbols, dtype=np.complex64)
+    if len(syms) == 0:
+        return np.zeros(0, np.complex128)
+    up = np.zeros((len(syms) - 1) * sps + 1, dtype=np.complex128)
+    up[::sps] = syms
+    return np.convolve(up, np.asarray(h, float), mode='full')
+
+
+def matched_filter(samples, h, sps):
+    """matched_filter (modulators.py:102-117): convolve(samples, h, 'full')[2*delay::sps] with
+    delay = (len(h)-1)//2; an empty complex64 array when the start index is past the end."""
+    samples = np.asarray(samples)
+    filtered = np.convolve(samples, np.asarray(h, float), mode='full') if len(samples) else np.zeros(0, np.complex128)
+    start = 2 * ((len(h) - 1) // 2)
+    if start >= len(filtered):
+        return np.array([], dtype=np.complex64)
+    return filtered[start::sps]

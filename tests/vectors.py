@@ -89,3 +89,22 @@ def noisy_symbols(syms, name):
     rs = np.random.RandomState(999 + BPS[name])
     sigma = {'BPSK': 0.5, 'QPSK': 0.4, '8PSK': 0.2, '16QAM': 0.15, '64QAM': 0.07, '256QAM': 0.03}[name]
     return np.asarray(syms).astype(np.complex128) + sigma * (rs.randn(len(syms)) + 1j * rs.randn(len(syms)))
+
+
+# ---- waveform stage (modulators.py:19-117): RRC pulse shaping and matched filter -------------------
+WAVEFORM_CASES = [(8, 0.35, 6), (4, 0.25, 8), (5, 0.5, 3)]       # (samples per symbol, roll-off, span in symbols)
+WAVEFORM_NSYM = 1000
+
+
+def waveform_symbols(sps):
+    """Seeded unit-power QPSK-like complex64 symbols."""
+    rs = np.random.RandomState(7000 + sps)
+    s = (rs.randint(0, 2, WAVEFORM_NSYM) * 2 - 1) + 1j * (rs.randint(0, 2, WAVEFORM_NSYM) * 2 - 1)
+    return (s / np.sqrt(2)).astype(np.complex64)
+
+
+def waveform_noise(shaped, sps):
+    """The received samples fed to the matched filter: the shaped waveform + seeded complex noise, complex64."""
+    rs = np.random.RandomState(7100 + sps)
+    n = 0.05 * (rs.randn(len(shaped)) + 1j * rs.randn(len(shaped)))
+    return (np.asarray(shaped) + n).astype(np.complex64)

@@ -45,6 +45,52 @@ pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__
     }
 }
 
+// Compile-time sps: a thread owns ALL sps output samples of one symbol period q — the Q = ceil(ntaps/sps) symbols
+// they depend on are loaded once (coalesced: consecutive threads, consecutive symbols) and the sps*Q complex MACs run
+// out of registers with broadcast tap reads; the thread's sps samples are 8*sps contiguous bytes, stored 16 B at a time.
+template <int SPS>
+__global__ void __launch_bounds__(256)
+pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__restrict__ taps, int ntaps,
+                       size_t n_out, float2 *__restrict__ out)
+{
+    constexpr int kMaxQ = 16;
+    extern __shared__ float sh[];                                   // taps, zero-padded to Q * SPS
+    const int Q = (ntaps + SPS - 1) / SPS;
+    for (int i = threadIdx.x; i < Q * SPS; i += blockDim.x) sh[i] = i < ntaps ? taps[i] : 0.f;
+    __syncthreads();
+    const size_t nq = (n_out + SPS - 1) / SPS;                      // symbol periods that hold output samples
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        float2 s[kMaxQ];
+#pragma unroll
+        for (int j = 0; j < kMaxQ; ++j)
+            s[j] = (j < Q && q >= (size_t)j && q - j < n_sym) ? __ldg(sym + (q - j)) : make_float2(0.f, 0.f);
+        float2 acc[SPS];
+#pragma unroll
+        for (int p = 0; p < SPS; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kMaxQ; ++j) {
+            if (j < Q) {
+#pragma unroll
+                for (int p = 0; p < SPS; ++p) {
+                    const float hh = sh[j * SPS + p];
+                    acc[p].x = fmaf(s[j].x, hh, acc[p].x);
+                    acc[p].y = fmaf(s[j].y, hh, acc[p].y);
+                }
+            }
+        }
+        float2 *o = out + q * SPS;
+        if ((q + 1) * SPS <= n_out && (SPS % 2) == 0) {             // whole period in range: 16-byte stores (q*SPS*8 B is 16-aligned)
+#pragma unroll
+            for (int p = 0; p < SPS; p += 2)
+                *reinterpret_cast<float4 *>(o + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
+        } else {
+#pragma unroll
+            for (int p = 0; p < SPS; ++p)
+                if (q * SPS + p < n_out) o[p] = acc[p];
+        }
+    }
+}
+
 // out[m] = sum_t h[t] * x[start + m*sps - t],  x[i] = 0 outside [0, n)
 __global__ void __launch_bounds__(kMfTile)
 matched_filter_kernel(size_t n, const float2 *__restrict__ x, const float *__restrict__ taps, int ntaps,
@@ -71,11 +117,16 @@ matched_filter_kernel(size_t n, const float2 *__restrict__ x, const float *__res
         const size_t m = m0 + threadIdx.x;
         const int r0 = (int)(start + (long long)m0 * sps - base);   // staged index of this tile's first output sample
         float ar = 0.f, ai = 0.f;
+        // staged index of tap t for this thread: r0 - t (+ threadIdx.x * sps): phase and position walk down by one
+        // sample per tap — warp-uniform bookkeeping, no division in the loop
+        int ph = r0 % sps, off = ph * pitch + r0 / sps + threadIdx.x;
+#pragma unroll 7
         for (int t = 0; t < ntaps; ++t) {
-            const int r = r0 - t;                                   // >= 0 by construction of base
-            const float2 v = xs[(r % sps) * pitch + r / sps + threadIdx.x];
+            const float2 v = xs[off];
             ar = fmaf(v.x, h[t], ar);
             ai = fmaf(v.y, h[t], ai);
+            if (ph == 0) { ph = sps - 1; off += (sps - 1) * pitch - 1; }    // previous sample: last phase, one position back
+            else         { --ph; off -= pitch; }
         }
         if (m < n_out) out[m] = make_float2(ar, ai);
     }
@@ -90,6 +141,20 @@ int launch_pulse_shape(size_t n_sym, const void *sym, const float *taps, int nta
     int dev = 0, sms = 148;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int Q = (ntaps + sps - 1) / sps;
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if ((sps == 8 || sps == 4 || sps == 2) && Q <= 16 && al16) {
+        size_t blocks = ((n_out + sps - 1) / sps + 255) / 256;
+        if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
+        const size_t smem = (size_t)Q * sps * sizeof(float);
+        const float2 *sy = reinterpret_cast<const float2 *>(sym);
+        float2 *o = reinterpret_cast<float2 *>(out);
+        if (sps == 8)      pulse_shape_sps_kernel<8><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
+        else if (sps == 4) pulse_shape_sps_kernel<4><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
+        else               pulse_shape_sps_kernel<2><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
+        B2_CUDA(cudaGetLastError());
+        return B200DVB_OK;
+    }
     size_t blocks = (n_out + 255) / 256;
     if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
     pulse_shape_kernel<<<(unsigned)blocks, 256, ntaps * sizeof(float), s>>>(

@@ -159,15 +159,16 @@ int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
 int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
                          unsigned long long offset, void *iq, void *stream);
 
-/* Waveform stage next to the mapper / demapper (float32 FMAs, taps float32[ntaps] on the device).
+/* Waveform stage next to the mapper / demapper (float32 FMAs; taps_h = HOST float64[ntaps], the
+ * reference's rrc_filter array, ntaps <= 448: they travel in the kernel's parameter space).
  * Pulse shaping = scipy.signal.upfirdn(taps, sym, up=sps) as modulators.py:85-100 calls it:
  *   out[i] = sum_k sym[k] * taps[i - k*sps],  out float2[(n_sym-1)*sps + ntaps]. */
-int b200dvb_pulse_shape(size_t n_sym, const void *sym, const float *taps, int ntaps, int sps,
+int b200dvb_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int ntaps, int sps,
                         void *out, void *stream);
 /* Matched filter + decimation = convolve(samples, taps, 'full')[start::sps] (modulators.py:102-117 with
  * start = 2*filter_delay; sdr_modem.py:558 is the same FIR):
  *   out[m] = sum_t taps[t] * samples[start + m*sps - t]  (samples outside [0, n) read as 0),  out float2[n_out]. */
-int b200dvb_matched_filter(size_t n, const void *samples, const float *taps, int ntaps, int sps,
+int b200dvb_matched_filter(size_t n, const void *samples, const double *taps_h, int ntaps, int sps,
                            long long start, size_t n_out, void *out, void *stream);
 
 /* Diagnostics: SM cycles the decoder CTAs spent per phase since the last reset, summed

@@ -276,18 +276,18 @@ int b200dvb_awgn_complex(size_t n_sym, float sigma, unsigned long long seed,
     return launch_awgn_complex(n_sym, sigma, seed, offset, iq, (cudaStream_t)stream);
 }
 
-int b200dvb_pulse_shape(size_t n_sym, const void *sym, const float *taps, int ntaps, int sps, void *out, void *stream)
+int b200dvb_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int ntaps, int sps, void *out, void *stream)
 {
-    if (!sym || !taps || !out || ntaps < 1 || ntaps > 4096 || sps < 1 || sps > 64) return B200DVB_EINVAL;
-    return launch_pulse_shape(n_sym, sym, taps, ntaps, sps, out, (cudaStream_t)stream);
+    if (!sym || !taps_h || !out || ntaps < 1 || ntaps > kMaxFirTaps || sps < 1 || sps > 64) return B200DVB_EINVAL;
+    return launch_pulse_shape(n_sym, sym, taps_h, ntaps, sps, out, (cudaStream_t)stream);
 }
 
-int b200dvb_matched_filter(size_t n, const void *samples, const float *taps, int ntaps, int sps, long long start,
+int b200dvb_matched_filter(size_t n, const void *samples, const double *taps_h, int ntaps, int sps, long long start,
                            size_t n_out, void *out, void *stream)
 {
-    if (!samples || !taps || (!out && n_out) || ntaps < 1 || ntaps > 4096 || sps < 1 || sps > 64 || start < 0)
+    if (!samples || !taps_h || (!out && n_out) || ntaps < 1 || ntaps > kMaxFirTaps || sps < 1 || sps > 64 || start < 0)
         return B200DVB_EINVAL;
-    return launch_matched_filter(n, samples, taps, ntaps, sps, start, n_out, out, (cudaStream_t)stream);
+    return launch_matched_filter(n, samples, taps_h, ntaps, sps, start, n_out, out, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -123,8 +123,9 @@ int launch_demap(const Modem &m, size_t n, const void *iq, float noise_var, floa
                  float *llr, cudaStream_t s);
 int launch_hard(const Modem &m, size_t n, const void *iq, int in_f64, uint8_t *bits, cudaStream_t s);
 
-int launch_pulse_shape(size_t n_sym, const void *sym, const float *taps, int ntaps, int sps, void *out, cudaStream_t s);
-int launch_matched_filter(size_t n, const void *x, const float *taps, int ntaps, int sps, long long start,
+constexpr int kMaxFirTaps = 448;    // FIR taps travel in the kernel parameter space (constant bank): 8 B per tap of 4 KB
+int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int ntaps, int sps, void *out, cudaStream_t s);
+int launch_matched_filter(size_t n, const void *x, const double *taps_h, int ntaps, int sps, long long start,
                           size_t n_out, void *out, cudaStream_t s);
 
 int modem_build_pwl(Modem &m);

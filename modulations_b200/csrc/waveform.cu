@@ -6,13 +6,15 @@
 //   pulse shaping   8 B of symbol in, 8*sps B of samples out per symbol: write bound.  Polyphase:
 //                   out[q*sps + p] = sum_j s[q-j] * h[p + j*sps]; a thread owns one output sample,
 //                   the <= ceil(ntaps/sps) symbols it needs are shared by the sps threads around it
-//                   (L1), the taps sit in shared memory.
+//                   (L1); for sps 2/4/8 a thread owns a whole symbol period instead (see below).
 //   matched filter  8*sps B of samples in, 8 B of symbol out per symbol: read bound.  A block owns
 //                   256 consecutive outputs; the samples they span are staged in shared memory
 //                   PHASE-MAJOR ([i mod sps][i / sps]): for a given tap every thread of a warp then
 //                   reads consecutive 8-byte words (no bank conflicts — sample-major staging would be
 //                   a 2*sps-word stride), and every input sample is read from HBM exactly once.
 //
+// The taps arrive as a HOST float64 array (the reference's rrc_filter), are rounded once to float32 and travel in the
+// kernel's parameter space (constant bank).
 // Arithmetic: float32 FMAs, taps rounded once to float32; the reference convolves in float64, so
 // parity is a stated tolerance (tests/test_gpu_waveform.py), not bit-exactness.
 #include "common.cuh"
@@ -23,13 +25,17 @@ namespace {
 
 constexpr int kMfTile = 256;        // outputs per block = threads per block
 
+// Taps travel as a kernel argument: the parameter space is a constant bank, so a tap (and, for the matched filter,
+// the staged offset of the sample it multiplies) is a uniform constant-cache read, not a shared-memory wavefront.
+struct FirTaps {
+    float h[kMaxFirTaps];
+    int off[kMaxFirTaps];           // matched filter: staged offset of tap t for thread 0 (see matched_filter_kernel)
+};
+
 __global__ void __launch_bounds__(256)
-pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__restrict__ taps, int ntaps,
+pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const __grid_constant__ FirTaps T, int ntaps,
                    int sps, size_t n_out, float2 *__restrict__ out)
 {
-    extern __shared__ float sh[];
-    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) sh[i] = taps[i];
-    __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
         const size_t q = i / sps;
         const int p = (int)(i - q * sps);
@@ -37,8 +43,8 @@ pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__
         for (int j = 0, t = p; t < ntaps; ++j, t += sps) {
             if (q >= (size_t)j && q - j < n_sym) {
                 const float2 s = __ldg(sym + (q - j));
-                ar = fmaf(s.x, sh[t], ar);
-                ai = fmaf(s.y, sh[t], ai);
+                ar = fmaf(s.x, T.h[t], ar);
+                ai = fmaf(s.y, T.h[t], ai);
             }
         }
         out[i] = make_float2(ar, ai);
@@ -47,17 +53,14 @@ pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__
 
 // Compile-time sps: a thread owns ALL sps output samples of one symbol period q — the Q = ceil(ntaps/sps) symbols
 // they depend on are loaded once (coalesced: consecutive threads, consecutive symbols) and the sps*Q complex MACs run
-// out of registers with broadcast tap reads; the thread's sps samples are 8*sps contiguous bytes, stored 16 B at a time.
+// out of registers; the thread's sps samples are 8*sps contiguous bytes, stored 16 B at a time.  T.h is zero beyond ntaps.
 template <int SPS>
 __global__ void __launch_bounds__(256)
-pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const float *__restrict__ taps, int ntaps,
+pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const __grid_constant__ FirTaps T, int ntaps,
                        size_t n_out, float2 *__restrict__ out)
 {
     constexpr int kMaxQ = 16;
-    extern __shared__ float sh[];                                   // taps, zero-padded to Q * SPS
     const int Q = (ntaps + SPS - 1) / SPS;
-    for (int i = threadIdx.x; i < Q * SPS; i += blockDim.x) sh[i] = i < ntaps ? taps[i] : 0.f;
-    __syncthreads();
     const size_t nq = (n_out + SPS - 1) / SPS;                      // symbol periods that hold output samples
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
         float2 s[kMaxQ];
@@ -72,7 +75,7 @@ pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const float
             if (j < Q) {
 #pragma unroll
                 for (int p = 0; p < SPS; ++p) {
-                    const float hh = sh[j * SPS + p];
+                    const float hh = T.h[j * SPS + p];
                     acc[p].x = fmaf(s[j].x, hh, acc[p].x);
                     acc[p].y = fmaf(s[j].y, hh, acc[p].y);
                 }
@@ -91,86 +94,104 @@ pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const float
     }
 }
 
-// out[m] = sum_t h[t] * x[start + m*sps - t],  x[i] = 0 outside [0, n)
+// out[m] = sum_t h[t] * x[start + m*sps - t],  x[i] = 0 outside [0, n).
+// Staging is phase-major: sample i of the tile sits at xs[((i - base) mod sps) * pitch + (i - base) / sps] with base a
+// multiple of sps, so that for one tap the threads of a warp (consecutive outputs, i.e. samples sps apart) read
+// consecutive 8-byte words.  The staged index of the sample that tap t multiplies for the tile's first output is
+// r0 - t with r0 = ntaps - 1 + ((start - ntaps + 1) mod sps) — the same for every tile — so its offset T.off[t] is a
+// per-launch constant the host tabulates.
 __global__ void __launch_bounds__(kMfTile)
-matched_filter_kernel(size_t n, const float2 *__restrict__ x, const float *__restrict__ taps, int ntaps,
-                      int sps, long long start, size_t n_out, float2 *__restrict__ out, int pitch)
+matched_filter_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirTaps T, int ntaps,
+                      int sps, long long start, size_t n_out, float2 *__restrict__ out, int pitch, int r0)
 {
-    extern __shared__ float sh[];
-    float *h = sh;                                                  // [ntaps]
-    float2 *xs = reinterpret_cast<float2 *>(sh + ((ntaps + 1) & ~1)); // [sps][pitch], phase-major
-    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) h[i] = taps[i];
+    extern __shared__ float2 xs[];                                  // [sps][pitch], phase-major
+    const bool even = (kMfTile % sps) == 0;                         // then a thread's phase never changes while staging
     for (size_t m0 = (size_t)blockIdx.x * kMfTile; m0 < n_out; m0 += (size_t)gridDim.x * kMfTile) {
-        // samples spanned by outputs m0 .. m0 + 255: [lo, hi]; the staging origin is lo rounded DOWN to a multiple
-        // of sps so that (i - base) mod sps is the phase of sample i for every block
-        const long long hi = start + (long long)(m0 + kMfTile - 1) * sps;
-        const long long lo = start + (long long)m0 * sps - (ntaps - 1);
-        const long long base = (lo >= 0 ? lo / sps : -((-lo + sps - 1) / sps)) * sps;
-        const int span = (int)(hi - base + 1);
+        const long long base = start + (long long)m0 * sps - r0;    // staged index 0 <-> sample `base` (a multiple of sps)
+        const int span = (kMfTile - 1) * sps + r0 + 1;
         __syncthreads();                                            // previous tile fully consumed
-        for (int r = threadIdx.x; r < span; r += blockDim.x) {
-            const long long i = base + r;
-            const float2 v = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
-            xs[(r % sps) * pitch + r / sps] = v;
+        if (even) {
+            const int ph = threadIdx.x % sps, step = kMfTile / sps;
+            int pos = threadIdx.x / sps;
+            for (int r = threadIdx.x; r < span; r += kMfTile, pos += step) {
+                const long long i = base + r;
+                xs[ph * pitch + pos] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+            }
+        } else {
+            for (int r = threadIdx.x; r < span; r += kMfTile) {
+                const long long i = base + r;
+                xs[(r % sps) * pitch + r / sps] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+            }
         }
         __syncthreads();
-        const size_t m = m0 + threadIdx.x;
-        const int r0 = (int)(start + (long long)m0 * sps - base);   // staged index of this tile's first output sample
-        float ar = 0.f, ai = 0.f;
-        // staged index of tap t for this thread: r0 - t (+ threadIdx.x * sps): phase and position walk down by one
-        // sample per tap — warp-uniform bookkeeping, no division in the loop
-        int ph = r0 % sps, off = ph * pitch + r0 / sps + threadIdx.x;
-#pragma unroll 7
-        for (int t = 0; t < ntaps; ++t) {
-            const float2 v = xs[off];
-            ar = fmaf(v.x, h[t], ar);
-            ai = fmaf(v.y, h[t], ai);
-            if (ph == 0) { ph = sps - 1; off += (sps - 1) * pitch - 1; }    // previous sample: last phase, one position back
-            else         { --ph; off -= pitch; }
+        const float2 *xt = xs + threadIdx.x;
+        float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;               // two accumulator pairs: shorter FMA chains
+        int t = 0;
+        for (; t + 2 <= ntaps; t += 2) {
+            const float2 v0 = xt[T.off[t]], v1 = xt[T.off[t + 1]];
+            ar = fmaf(v0.x, T.h[t], ar); ai = fmaf(v0.y, T.h[t], ai);
+            br = fmaf(v1.x, T.h[t + 1], br); bi = fmaf(v1.y, T.h[t + 1], bi);
         }
-        if (m < n_out) out[m] = make_float2(ar, ai);
+        if (t < ntaps) {
+            const float2 v0 = xt[T.off[t]];
+            ar = fmaf(v0.x, T.h[t], ar); ai = fmaf(v0.y, T.h[t], ai);
+        }
+        const size_t m = m0 + threadIdx.x;
+        if (m < n_out) out[m] = make_float2(ar + br, ai + bi);
     }
+}
+
+int fill_taps(FirTaps &T, const double *taps_h, int ntaps)
+{
+    if (ntaps < 1 || ntaps > kMaxFirTaps) return B200DVB_EINVAL;
+    for (int i = 0; i < kMaxFirTaps; ++i) { T.h[i] = i < ntaps ? (float)taps_h[i] : 0.f; T.off[i] = 0; }
+    return B200DVB_OK;
 }
 
 }  // namespace
 
-int launch_pulse_shape(size_t n_sym, const void *sym, const float *taps, int ntaps, int sps, void *out, cudaStream_t s)
+int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int ntaps, int sps, void *out, cudaStream_t s)
 {
     if (n_sym == 0) return B200DVB_OK;
+    FirTaps T;
+    if (int rc = fill_taps(T, taps_h, ntaps)) return rc;
     const size_t n_out = (n_sym - 1) * (size_t)sps + ntaps;
     int dev = 0, sms = 148;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int Q = (ntaps + sps - 1) / sps;
     const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const float2 *sy = reinterpret_cast<const float2 *>(sym);
+    float2 *o = reinterpret_cast<float2 *>(out);
     if ((sps == 8 || sps == 4 || sps == 2) && Q <= 16 && al16) {
         size_t blocks = ((n_out + sps - 1) / sps + 255) / 256;
         if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
-        const size_t smem = (size_t)Q * sps * sizeof(float);
-        const float2 *sy = reinterpret_cast<const float2 *>(sym);
-        float2 *o = reinterpret_cast<float2 *>(out);
-        if (sps == 8)      pulse_shape_sps_kernel<8><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
-        else if (sps == 4) pulse_shape_sps_kernel<4><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
-        else               pulse_shape_sps_kernel<2><<<(unsigned)blocks, 256, smem, s>>>(n_sym, sy, taps, ntaps, n_out, o);
+        if (sps == 8)      pulse_shape_sps_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
+        else if (sps == 4) pulse_shape_sps_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
+        else               pulse_shape_sps_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
         B2_CUDA(cudaGetLastError());
         return B200DVB_OK;
     }
     size_t blocks = (n_out + 255) / 256;
     if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
-    pulse_shape_kernel<<<(unsigned)blocks, 256, ntaps * sizeof(float), s>>>(
-        n_sym, reinterpret_cast<const float2 *>(sym), taps, ntaps, sps, n_out, reinterpret_cast<float2 *>(out));
+    pulse_shape_kernel<<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, sps, n_out, o);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }
 
-int launch_matched_filter(size_t n, const void *x, const float *taps, int ntaps, int sps, long long start,
+int launch_matched_filter(size_t n, const void *x, const double *taps_h, int ntaps, int sps, long long start,
                           size_t n_out, void *out, cudaStream_t s)
 {
     if (n_out == 0) return B200DVB_OK;
+    FirTaps T;
+    if (int rc = fill_taps(T, taps_h, ntaps)) return rc;
     // staged positions per phase: 256 outputs + the taps' reach + the rounding of the origin; odd pitch (in 8-byte
-    // words) keeps the sps rows of the staging pass in different banks
+    // words) spreads the sps rows of the staging pass over the banks
     const int pitch = (kMfTile + (ntaps + sps - 1) / sps + 2) | 1;
-    const size_t smem = (size_t)((ntaps + 1) & ~1) * sizeof(float) + (size_t)sps * pitch * sizeof(float2);
+    const long long lo = start - (ntaps - 1);                       // first sample of the first output
+    const int r0 = ntaps - 1 + (int)(((lo % sps) + sps) % sps);     // its staged index with the origin on a multiple of sps
+    for (int t = 0; t < ntaps; ++t) T.off[t] = ((r0 - t) % sps) * pitch + (r0 - t) / sps;
+    const size_t smem = (size_t)sps * pitch * sizeof(float2);
     if (smem > 200 * 1024) return B200DVB_EINVAL;
     int dev = 0, sms = 148;
     B2_CUDA(cudaGetDevice(&dev));
@@ -180,7 +201,7 @@ int launch_matched_filter(size_t n, const void *x, const float *taps, int ntaps,
     size_t blocks = (n_out + kMfTile - 1) / kMfTile;
     if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
     matched_filter_kernel<<<(unsigned)blocks, kMfTile, smem, s>>>(
-        n, reinterpret_cast<const float2 *>(x), taps, ntaps, sps, start, n_out, reinterpret_cast<float2 *>(out), pitch);
+        n, reinterpret_cast<const float2 *>(x), T, ntaps, sps, start, n_out, reinterpret_cast<float2 *>(out), pitch, r0);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

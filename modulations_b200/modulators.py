@@ -62,14 +62,12 @@ class Modulator:
         self.rrc_filter = rrcosfilter(self.rrc_span, self.rrc_alpha, 1, self.sps)
         self.filter_delay = (len(self.rrc_filter) - 1) // 2
         self._h = {}
-        self._taps_dev = None
 
     # ============ PULSE SHAPING (modulators.py:85-117) ============
     def _taps(self):
-        if self._taps_dev is None:
-            torch = _lib.require_cuda()
-            self._taps_dev = _lib.to_device(self.rrc_filter.astype(np.float32), torch.float32)
-        return self._taps_dev
+        """the reference's float64 tap array, as the C ABI takes it (a host pointer)"""
+        self._taps_h = np.ascontiguousarray(self.rrc_filter, np.float64)
+        return _lib.host_ptr(self._taps_h)
 
     def apply_pulse_shaping(self, symbols):
         """Upsample by ``sps`` and apply the TX RRC filter: ``upfirdn(rrc_filter, complex64(symbols), up=sps)``
@@ -81,7 +79,7 @@ class Modulator:
         n, nt = s.numel(), len(self.rrc_filter)
         out = torch.empty((n - 1) * self.sps + nt if n else 0, dtype=torch.complex64, device=s.device)
         if n:
-            _lib.check(_lib.load().b200dvb_pulse_shape(n, _lib.ptr(s), _lib.ptr(self._taps()), nt, self.sps,
+            _lib.check(_lib.load().b200dvb_pulse_shape(n, _lib.ptr(s), self._taps(), nt, self.sps,
                                                        _lib.ptr(out), _lib.stream_ptr()), "pulse_shape")
         return out if is_torch else out.cpu().numpy().astype(np.complex128)
 
@@ -98,7 +96,7 @@ class Modulator:
             return torch.empty(0, dtype=torch.complex64, device=x.device) if is_torch else np.array([], dtype=np.complex64)
         n_out = (full - start + self.sps - 1) // self.sps
         out = torch.empty(n_out, dtype=torch.complex64, device=x.device)
-        _lib.check(_lib.load().b200dvb_matched_filter(n, _lib.ptr(x), _lib.ptr(self._taps()), nt, self.sps, start,
+        _lib.check(_lib.load().b200dvb_matched_filter(n, _lib.ptr(x), self._taps(), nt, self.sps, start,
                                                       n_out, _lib.ptr(out), _lib.stream_ptr()), "matched_filter")
         return out if is_torch else out.cpu().numpy().astype(np.complex128)
 

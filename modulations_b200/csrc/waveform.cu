@@ -8,7 +8,7 @@
 //                   the <= ceil(ntaps/sps) symbols it needs are shared by the sps threads around it
 //                   (L1); for sps 2/4/8 a thread owns a whole symbol period instead (see below).
 //   matched filter  8*sps B of samples in, 8 B of symbol out per symbol: read bound.  A block owns
-//                   256 consecutive outputs; the samples they span are staged in shared memory
+//                   512 consecutive outputs (two per thread); the samples they span are staged in shared memory
 //                   PHASE-MAJOR ([i mod sps][i / sps]): for a given tap every thread of a warp then
 //                   reads consecutive 8-byte words (no bank conflicts — sample-major staging would be
 //                   a 2*sps-word stride), and every input sample is read from HBM exactly once.
@@ -23,7 +23,8 @@ namespace b200dvb {
 
 namespace {
 
-constexpr int kMfTile = 256;        // outputs per block = threads per block
+constexpr int kMfThreads = 256;
+constexpr int kMfTile = 512;        // outputs per block: two per thread (the constant reads and the loop are shared)
 
 // Taps travel as a kernel argument: the parameter space is a constant bank, so a tap (and, for the matched filter,
 // the staged offset of the sample it multiplies) is a uniform constant-cache read, not a shared-memory wavefront.
@@ -82,7 +83,14 @@ pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const __gri
             }
         }
         float2 *o = out + q * SPS;
-        if ((q + 1) * SPS <= n_out && (SPS % 2) == 0) {             // whole period in range: 16-byte stores (q*SPS*8 B is 16-aligned)
+        if ((q + 1) * SPS <= n_out && (SPS % 4) == 0) {             // whole period in range: 32-byte stores = full sectors
+#pragma unroll                                                      // (out is 32-byte aligned on this path)
+            for (int p = 0; p < SPS; p += 4)
+                asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "l"(o + p), "f"(acc[p].x), "f"(acc[p].y), "f"(acc[p + 1].x), "f"(acc[p + 1].y),
+                                "f"(acc[p + 2 < SPS ? p + 2 : p].x), "f"(acc[p + 2 < SPS ? p + 2 : p].y),
+                                "f"(acc[p + 3 < SPS ? p + 3 : p].x), "f"(acc[p + 3 < SPS ? p + 3 : p].y) : "memory");
+        } else if ((q + 1) * SPS <= n_out && (SPS % 2) == 0) {
 #pragma unroll
             for (int p = 0; p < SPS; p += 2)
                 *reinterpret_cast<float4 *>(o + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
@@ -100,44 +108,51 @@ pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const __gri
 // consecutive 8-byte words.  The staged index of the sample that tap t multiplies for the tile's first output is
 // r0 - t with r0 = ntaps - 1 + ((start - ntaps + 1) mod sps) — the same for every tile — so its offset T.off[t] is a
 // per-launch constant the host tabulates.
-__global__ void __launch_bounds__(kMfTile)
+__global__ void __launch_bounds__(kMfThreads)
 matched_filter_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirTaps T, int ntaps,
                       int sps, long long start, size_t n_out, float2 *__restrict__ out, int pitch, int r0)
 {
     extern __shared__ float2 xs[];                                  // [sps][pitch], phase-major
-    const bool even = (kMfTile % sps) == 0;                         // then a thread's phase never changes while staging
+    const bool even = (kMfThreads % sps) == 0;                      // then a thread's phase never changes while staging
     for (size_t m0 = (size_t)blockIdx.x * kMfTile; m0 < n_out; m0 += (size_t)gridDim.x * kMfTile) {
         const long long base = start + (long long)m0 * sps - r0;    // staged index 0 <-> sample `base` (a multiple of sps)
         const int span = (kMfTile - 1) * sps + r0 + 1;
         __syncthreads();                                            // previous tile fully consumed
         if (even) {
-            const int ph = threadIdx.x % sps, step = kMfTile / sps;
+            // eight loads in flight per thread before the first shared-memory store: the staging pass is the only
+            // place this kernel touches HBM, and a rolled load-store loop would pay one memory latency per iteration
+            const int ph = threadIdx.x % sps, step = kMfThreads / sps;
             int pos = threadIdx.x / sps;
-            for (int r = threadIdx.x; r < span; r += kMfTile, pos += step) {
-                const long long i = base + r;
-                xs[ph * pitch + pos] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+            for (int r = threadIdx.x; r < span; r += 8 * kMfThreads, pos += 8 * step) {
+                float2 buf[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long i = base + r + u * kMfThreads;
+                    buf[u] = (r + u * kMfThreads < span && i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r + u * kMfThreads < span) xs[ph * pitch + pos + u * step] = buf[u];
             }
         } else {
-            for (int r = threadIdx.x; r < span; r += kMfTile) {
+            for (int r = threadIdx.x; r < span; r += kMfThreads) {
                 const long long i = base + r;
                 xs[(r % sps) * pitch + r / sps] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
             }
         }
         __syncthreads();
-        const float2 *xt = xs + threadIdx.x;
-        float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;               // two accumulator pairs: shorter FMA chains
-        int t = 0;
-        for (; t + 2 <= ntaps; t += 2) {
-            const float2 v0 = xt[T.off[t]], v1 = xt[T.off[t + 1]];
-            ar = fmaf(v0.x, T.h[t], ar); ai = fmaf(v0.y, T.h[t], ai);
-            br = fmaf(v1.x, T.h[t + 1], br); bi = fmaf(v1.y, T.h[t + 1], bi);
-        }
-        if (t < ntaps) {
-            const float2 v0 = xt[T.off[t]];
-            ar = fmaf(v0.x, T.h[t], ar); ai = fmaf(v0.y, T.h[t], ai);
+        const float2 *xt = xs + threadIdx.x;                        // outputs m0 + tid and m0 + tid + 256
+        float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+        for (int t = 0; t < ntaps; ++t) {
+            const int o = T.off[t];
+            const float hh = T.h[t];
+            const float2 v0 = xt[o], v1 = xt[o + kMfThreads];
+            ar = fmaf(v0.x, hh, ar); ai = fmaf(v0.y, hh, ai);
+            br = fmaf(v1.x, hh, br); bi = fmaf(v1.y, hh, bi);
         }
         const size_t m = m0 + threadIdx.x;
-        if (m < n_out) out[m] = make_float2(ar + br, ai + bi);
+        if (m < n_out) out[m] = make_float2(ar, ai);
+        if (m + kMfThreads < n_out) out[m + kMfThreads] = make_float2(br, bi);
     }
 }
 
@@ -160,7 +175,7 @@ int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int 
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int Q = (ntaps + sps - 1) / sps;
-    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;   // 32-byte stores on the per-period path
     const float2 *sy = reinterpret_cast<const float2 *>(sym);
     float2 *o = reinterpret_cast<float2 *>(out);
     if ((sps == 8 || sps == 4 || sps == 2) && Q <= 16 && al16) {
@@ -200,7 +215,7 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
         B2_CUDA(cudaFuncSetAttribute(matched_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t blocks = (n_out + kMfTile - 1) / kMfTile;
     if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
-    matched_filter_kernel<<<(unsigned)blocks, kMfTile, smem, s>>>(
+    matched_filter_kernel<<<(unsigned)blocks, kMfThreads, smem, s>>>(
         n, reinterpret_cast<const float2 *>(x), T, ntaps, sps, start, n_out, reinterpret_cast<float2 *>(out), pitch, r0);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;

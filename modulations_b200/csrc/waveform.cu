@@ -11,7 +11,8 @@
 //                   512 consecutive outputs (two per thread); the samples they span are staged in shared memory
 //                   PHASE-MAJOR ([i mod sps][i / sps]): for a given tap every thread of a warp then
 //                   reads consecutive 8-byte words (no bank conflicts — sample-major staging would be
-//                   a 2*sps-word stride), and every input sample is read from HBM exactly once.
+//                   a 2*sps-word stride), and every input sample is read from HBM once (plus the taps' reach
+//                   at tile boundaries: 48 of 4140 samples at sps 8).
 //
 // The taps arrive as a HOST float64 array (the reference's rrc_filter), are rounded once to float32 and travel in the
 // kernel's parameter space (constant bank).

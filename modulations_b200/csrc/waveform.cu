@@ -109,17 +109,37 @@ pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const __gri
 // consecutive 8-byte words.  The staged index of the sample that tap t multiplies for the tile's first output is
 // r0 - t with r0 = ntaps - 1 + ((start - ntaps + 1) mod sps) — the same for every tile — so its offset T.off[t] is a
 // per-launch constant the host tabulates.
-__global__ void __launch_bounds__(kMfThreads)
+__global__ void __launch_bounds__(kMfThreads, 4)
 matched_filter_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirTaps T, int ntaps,
                       int sps, long long start, size_t n_out, float2 *__restrict__ out, int pitch, int r0)
 {
     extern __shared__ float2 xs[];                                  // [sps][pitch], phase-major
     const bool even = (kMfThreads % sps) == 0;                      // then a thread's phase never changes while staging
+    const bool fast = even && (sps % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     for (size_t m0 = (size_t)blockIdx.x * kMfTile; m0 < n_out; m0 += (size_t)gridDim.x * kMfTile) {
         const long long base = start + (long long)m0 * sps - r0;    // staged index 0 <-> sample `base` (a multiple of sps)
         const int span = (kMfTile - 1) * sps + r0 + 1;
         __syncthreads();                                            // previous tile fully consumed
-        if (even) {
+        if (fast && base >= 0 && (size_t)(base + span + 1) <= n) {
+            // interior tile, even sps, 16-byte aligned input: 16-byte loads (two samples: phases ph, ph + 1 of the same
+            // position), all of a thread's loads in flight before its first shared-memory store, 32-bit indexing
+            const float2 *xb = x + base;
+            const int ph = (2 * threadIdx.x) % sps, step = 2 * kMfThreads / sps;
+            const int pos0 = (2 * threadIdx.x) / sps;
+            constexpr int kIt = 5;                                  // loads in flight per thread and pass
+            for (int r = 2 * threadIdx.x, pos = pos0; r < span; r += kIt * 2 * kMfThreads, pos += kIt * step) {
+                float4 buf[kIt];
+#pragma unroll
+                for (int u = 0; u < kIt; ++u)
+                    if (r + u * 2 * kMfThreads < span) buf[u] = __ldg(reinterpret_cast<const float4 *>(xb + r + u * 2 * kMfThreads));
+#pragma unroll
+                for (int u = 0; u < kIt; ++u)
+                    if (r + u * 2 * kMfThreads < span) {
+                        xs[ph * pitch + pos + u * step] = make_float2(buf[u].x, buf[u].y);
+                        xs[(ph + 1) * pitch + pos + u * step] = make_float2(buf[u].z, buf[u].w);
+                    }
+            }
+        } else if (even) {
             // eight loads in flight per thread before the first shared-memory store: the staging pass is the only
             // place this kernel touches HBM, and a rolled load-store loop would pay one memory latency per iteration
             const int ph = threadIdx.x % sps, step = kMfThreads / sps;

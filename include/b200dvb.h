@@ -189,6 +189,9 @@ int b200dvb_tmem_selftest(int *errors_h);
 /* Small device-throughput probes used by bench.py to state the ALU roofline
  * (FADD / FMNMX / SHFL lane-ops per clock per SM).  results_h: double[8]. */
 int b200dvb_microbench(double *results_h);
+/* Packed 16-bit / DPX probes for the non-parity decoder modes (lane-instructions per clock per SM;
+ * layout in csrc/microbench.cu).  results16_h: double[16]. */
+int b200dvb_microbench2(double *results16_h);
 
 #ifdef __cplusplus
 }

@@ -393,4 +393,10 @@ int b200dvb_microbench(double *results_h)
     return run_microbench(results_h);
 }
 
+int b200dvb_microbench2(double *results16_h)
+{
+    if (!results16_h) return B200DVB_EINVAL;
+    return run_microbench2(results16_h);
+}
+
 }  // extern "C"

@@ -130,6 +130,7 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
 
 int modem_build_pwl(Modem &m);
 int run_microbench(double *results_h);
+int run_microbench2(double *results16_h);
 int run_tmem_selftest(int *result_h);
 
 }  // namespace b200dvb

@@ -181,3 +181,124 @@ int run_tmem_selftest(int *result_h)
 }
 
 }  // namespace b200dvb
+
+// ---------------------------------------------------------------------------
+// Second probe set: packed 16-bit arithmetic for the non-parity decoder modes: is an
+// add-compare-select in f16x2 / s16x2 (two frames per lane) or as a DPX VIADDMNMX cheaper per ACS than
+// the FADD + FMNMX pair of the parity decoder?  results16[] in lane-INSTRUCTIONS per clock per SM (a
+// packed instruction counts once):
+//  0 add.f16x2   1 max.f16x2   2 step mix f16x2 (2 add + 1 max + 1 sub)   3 step mix f32 (same shape)
+//  4 add.s32     5 max.s32     6 viaddmax.s32 (DPX)   7 add.s16x2   8 max.s16x2   9 viaddmax.s16x2 (DPX)
+// 10 step mix s16x2 (add + viaddmax + sub)   11 step mix s32 (add + viaddmax + sub)   12..15 reserved
+// ---------------------------------------------------------------------------
+#include <cuda_fp16.h>
+namespace b200dvb {
+namespace {
+
+template <int OP>
+__global__ void __launch_bounds__(1024) probe2(unsigned seed, long long *cycles, unsigned *sink)
+{
+    unsigned x[kChains];
+    float f[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) { x[i] = seed * 0x3c003c00u + i + threadIdx.x; f[i] = (float)(seed + i); }
+    const unsigned c = seed * 0x34003400u, c2 = seed * 0x30003000u;
+    const float fc = seed * 0.5f, fc2 = seed * 0.25f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < kIter; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            const int j = (i + 1) % kChains;
+            if (OP == 0) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 1) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 2) {
+                unsigned a, b, m;
+                asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(x[i]), "r"(c));
+                asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(b) : "r"(x[j]), "r"(c2));
+                asm volatile("max.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+                asm volatile("sub.rn.f16x2 %0, %1, %2;" : "=r"(x[i]) : "r"(m), "r"(c2));
+            }
+            if (OP == 3) {
+                float a, b, m;
+                asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(a) : "f"(f[i]), "f"(fc));
+                asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(b) : "f"(f[j]), "f"(fc2));
+                asm volatile("max.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+                asm volatile("sub.rn.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(m), "f"(fc2));
+            }
+            if (OP == 4) asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 5) asm volatile("max.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 6) x[i] = (unsigned)__viaddmax_s32((int)x[i], (int)c, (int)c2);
+            if (OP == 7) asm volatile("add.s16x2 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 8) asm volatile("max.s16x2 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            if (OP == 9) x[i] = __viaddmax_s16x2(x[i], c, c2);
+            if (OP == 10) {
+                unsigned a, m;
+                asm volatile("add.s16x2 %0, %1, %2;" : "=r"(a) : "r"(x[i]), "r"(c));
+                m = __viaddmax_s16x2(x[j], c2, a);
+                asm volatile("add.s16x2 %0, %1, %2;" : "=r"(x[i]) : "r"(m), "r"(c));   // normalisation: add of the packed negated metric
+            }
+            if (OP == 11) {
+                int a = (int)x[i] + (int)c;
+                int m = __viaddmax_s32((int)x[j], (int)c2, a);
+                x[i] = (unsigned)(m - (int)c2);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    unsigned acc = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) acc += x[i] + __float_as_uint(f[i]);
+    if (acc == 0x12345u) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+int run_two(int sms, long long *d_cycles, unsigned *d_sink, double ops_per_iter, double *out)
+{
+    probe2<OP><<<sms, 1024>>>(1u, d_cycles, d_sink);
+    probe2<OP><<<sms, 1024>>>(1u, d_cycles, d_sink);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaDeviceSynchronize());
+    long long *h = (long long *)malloc(sizeof(long long) * sms);
+    B2_CUDA(cudaMemcpy(h, d_cycles, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < sms; ++i) avg += (double)h[i];
+    avg /= sms;
+    free(h);
+    *out = 1024.0 * kIter * kChains * ops_per_iter / avg;
+    return B200DVB_OK;
+}
+
+}  // namespace
+
+int run_microbench2(double *r)
+{
+    int dev = 0, sms = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long *d_cycles = nullptr;
+    unsigned *d_sink = nullptr;
+    B2_CUDA(cudaMalloc(&d_cycles, sizeof(long long) * sms));
+    B2_CUDA(cudaMalloc(&d_sink, sizeof(unsigned)));
+    for (int i = 0; i < 16; ++i) r[i] = 0.0;
+    int rc = B200DVB_OK;
+    if (rc == 0) rc = run_two<0>(sms, d_cycles, d_sink, 1, r + 0);
+    if (rc == 0) rc = run_two<1>(sms, d_cycles, d_sink, 1, r + 1);
+    if (rc == 0) rc = run_two<2>(sms, d_cycles, d_sink, 4, r + 2);
+    if (rc == 0) rc = run_two<3>(sms, d_cycles, d_sink, 4, r + 3);
+    if (rc == 0) rc = run_two<4>(sms, d_cycles, d_sink, 1, r + 4);
+    if (rc == 0) rc = run_two<5>(sms, d_cycles, d_sink, 1, r + 5);
+    if (rc == 0) rc = run_two<6>(sms, d_cycles, d_sink, 1, r + 6);
+    if (rc == 0) rc = run_two<7>(sms, d_cycles, d_sink, 1, r + 7);
+    if (rc == 0) rc = run_two<8>(sms, d_cycles, d_sink, 1, r + 8);
+    if (rc == 0) rc = run_two<9>(sms, d_cycles, d_sink, 1, r + 9);
+    if (rc == 0) rc = run_two<10>(sms, d_cycles, d_sink, 3, r + 10);
+    if (rc == 0) rc = run_two<11>(sms, d_cycles, d_sink, 3, r + 11);
+    cudaFree(d_cycles);
+    cudaFree(d_sink);
+    return rc;
+}
+
+}  // namespace b200dvb

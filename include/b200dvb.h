@@ -78,6 +78,16 @@ int b200dvb_codec_n_llr(b200dvb_codec_t codec);
  * Batches and pipeline chunks that are multiples of it leave no SM idle in the last wave. */
 int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec);
 
+/* Development / test switches of one codec handle (production code never needs them):
+ *   B200DVB_OPT_KERNEL          0 = automatic (per batch size), 1 = quad kernel, 2 = thread-per-frame kernel
+ *                               (B200DVB_ENOSPEC when the codec's N has no thread-per-frame geometry)
+ *   B200DVB_OPT_NO_ROW_STAGING  1 = thread-per-frame transposition without the cp.async row staging
+ *   B200DVB_OPT_PHASE_TIMERS    1 = launches add per-phase SM cycles to the b200dvb_debug_*_cycles counters */
+#define B200DVB_OPT_KERNEL          1
+#define B200DVB_OPT_NO_ROW_STAGING  2
+#define B200DVB_OPT_PHASE_TIMERS    3
+int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value);
+
 /* One SISO half-iteration for B independent frames.  Replaces bcjr_max_log_map
  * (dvb_rcs2_turbo.py:116-281; historic aliases bcjr_decode_circular /
  * max_log_map_decode).  Lc_* float32[B*N], La_* float64[B*N] (NULL = zeros),
@@ -147,7 +157,9 @@ int b200dvb_hard_demod(b200dvb_modem_t modem, size_t n_sym, const void *iq, int 
  * device, written straight into the decoder's input layout.
  *   info_out uint8[B][2N]; coded_out uint8[B][n_llr]; llr_out float32[B][n_llr]
  *   (contiguous rows).  BPSK: llr = 2y/sigma^2 clipped to +-50
- *   (turbo_test_suite.py:158-161). */
+ *   (turbo_test_suite.py:158-161).  The streams are keyed by the GLOBAL frame index frame_offset + i;
+ *   frame_offset must start on a whole Philox draw: frame_offset*2N a multiple of 16 and
+ *   frame_offset*n_llr a multiple of 4 (any multiple of 16 frames), else B200DVB_EINVAL. */
 int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
                              unsigned long long seed, unsigned long long frame_offset,
                              uint8_t *info_out, uint8_t *coded_out, float *llr_out,
@@ -177,9 +189,9 @@ int b200dvb_matched_filter(size_t n, const void *samples, const double *taps_h, 
 int b200dvb_debug_phase_cycles(double *out8_h, int reset);
 /* Same for the thread-per-frame kernel (summed over warps): {transpose-in, pass 1 first half
  * incl. prep, pass 1 second half, pass 2 to the crossing, out-phase windows in shared memory,
- * out-phase windows in tensor memory, hard decision, warp total}.  Only launches made while the
- * environment variable B200DVB_TPF_TIMERS is set run the instance of the kernel that keeps these
- * counters (the production instance has no clock reads); tools/tpf_perf.py shows the use. */
+ * out-phase windows in tensor memory, hard decision, warp total}.  Only launches of a codec with
+ * B200DVB_OPT_PHASE_TIMERS set run the instance of the kernel that keeps these counters (the
+ * production instance has no clock reads); tools/tpf_perf.py shows the use. */
 int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the

@@ -12,9 +12,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B200DVB_LIB") or os.path.join(_HERE, "libb200dvb.so")   # env override: development only
+LIB_PATH = os.path.join(_HERE, "libb200dvb.so")
 
 OK, EINVAL, ENOSPEC, ECUDA, ENOMEM, EMOD = 0, -1, -2, -3, -4, -5
+OPT_KERNEL, OPT_NO_ROW_STAGING, OPT_PHASE_TIMERS = 1, 2, 3
+KERNEL_AUTO, KERNEL_QUAD, KERNEL_TPF = 0, 1, 2
 MOD_IDS = {'BPSK': 0, 'QPSK': 1, '8PSK': 2, '16QAM': 3, '64QAM': 4, '256QAM': 5}
 BPS = {'BPSK': 1, 'QPSK': 2, '8PSK': 3, '16QAM': 4, '64QAM': 6, '256QAM': 8}
 
@@ -32,6 +34,7 @@ SIGNATURES = {
     "b200dvb_codec_n_llr": (_c_int, [_c_void_p]),
     "b200dvb_codec_frames_per_wave": (_c_int, [_c_void_p]),
     "b200dvb_codec_circular_lut": (_c_int, [_c_void_p, _c_void_p]),
+    "b200dvb_codec_set_option": (_c_int, [_c_void_p, _c_int, _c_int]),
     "b200dvb_siso_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "b200dvb_siso": (_c_int, [_c_void_p, _c_int] + [_c_void_p] * 6 + [_c_double] + [_c_void_p] * 3 + [_c_size_t, _c_void_p]),
     "b200dvb_decode_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
@@ -99,9 +102,10 @@ def require_cuda():
     return torch
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     torch = torch_mod()
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def to_device(x, dtype, device=None):

@@ -232,10 +232,38 @@ int b200dvb_siso(b200dvb_codec_t codec, int B, const float *Lc_A, const float *L
                        workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// Which decode kernel serves a batch of B frames.  The thread-per-frame kernel has the higher throughput but a
+// 16-frame tile takes as long as a full wave (64 frames per SM); the quad kernel finishes a wave of 32 frames per
+// SM in 0.72x that time (profiles/r02_measure_pack1.txt: 0.75 ms against 1.05 ms at N=212), so batches that fit one
+// quad wave go there.  A pure function of (codec, B): the workspace query and the launch agree.
+static bool use_tpf(const Codec &c, int B)
+{
+    if (!c.tpf.enabled || c.opt_kernel == 1) return false;
+    if (c.opt_kernel == 2) return true;
+    const long long quad_wave = (long long)c.num_sms * c.geom.ctas_per_sm * c.geom.frames;
+    return !(c.geom.frames <= 32 && B <= quad_wave);
+}
+
 size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B)
 {
     if (!codec || B <= 0) return 0;
-    return codec->c.tpf.enabled ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
+    return use_tpf(codec->c, B) ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
+}
+
+int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value)
+{
+    if (!codec) return B200DVB_EINVAL;
+    Codec &c = codec->c;
+    switch (option) {
+    case B200DVB_OPT_KERNEL:
+        if (value < 0 || value > 2) return B200DVB_EINVAL;
+        if (value == 2 && !c.tpf.enabled) return B200DVB_ENOSPEC;
+        c.opt_kernel = value;
+        return B200DVB_OK;
+    case B200DVB_OPT_NO_ROW_STAGING: c.opt_no_row_staging = value != 0; return B200DVB_OK;
+    case B200DVB_OPT_PHASE_TIMERS: c.opt_phase_timers = value != 0; return B200DVB_OK;
+    default: return B200DVB_EINVAL;
+    }
 }
 
 int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr_stride,
@@ -245,7 +273,7 @@ int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr
 {
     if (!codec || B < 0 || !llr || (B && !workspace)) return B200DVB_EINVAL;
     if (llr_stride < codec->c.n_llr) return B200DVB_EINVAL;
-    if (codec->c.tpf.enabled)
+    if (use_tpf(codec->c, B))
         return tpf_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
                                  workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters, workspace,
@@ -264,6 +292,11 @@ int b200dvb_mc_generate_bpsk(b200dvb_codec_t codec, int B, float noise_var,
                              uint8_t *info_out, uint8_t *coded_out, float *llr_out, void *stream)
 {
     if (!codec || B < 0 || !info_out || !coded_out || !llr_out || !(noise_var > 0.f))
+        return B200DVB_EINVAL;
+    // the Philox counters advance in whole draws (16 info bits, 4 LLRs): a shard may only start on a draw boundary,
+    // otherwise its streams would overlap the neighbouring shard's (montecarlo.ALIGN = 16 frames always satisfies this)
+    if ((frame_offset * (unsigned long long)(2 * codec->c.N)) % 16ull != 0 ||
+        (frame_offset * (unsigned long long)codec->c.n_llr) % 4ull != 0)
         return B200DVB_EINVAL;
     return launch_mc_bpsk(codec->c, B, noise_var, seed, frame_offset, info_out, coded_out, llr_out,
                           (cudaStream_t)stream);
@@ -330,7 +363,7 @@ int b200dvb_modem_create(int mod_id, const double *table_h, b200dvb_modem_t *out
         delete h;
         return B200DVB_ECUDA;
     }
-    if (m.separable && !getenv("B200DVB_FORCE_GENERIC_DEMAP")) {
+    if (m.separable) {
         int rc = modem_build_pwl(m);
         if (rc != B200DVB_OK) { cudaFree(m.d_table64); cudaFree(m.d_table32); delete h; return rc; }
     }

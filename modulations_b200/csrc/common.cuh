@@ -70,6 +70,10 @@ struct Codec {
     TpfGeom tpf{};
     int num_sms = 0;
     int vec_ab = 0, vec_wy = 0;   // (A,B) / (W,Y) LLR pairs are adjacent and even-aligned in the stream
+    // development / test switches (b200dvb_codec_set_option); all 0 in production
+    int opt_kernel = 0;           // 0: automatic choice per batch, 1: quad kernel, 2: thread-per-frame kernel
+    int opt_no_row_staging = 0;   // 1: thread-per-frame transposition without the cp.async row staging
+    int opt_phase_timers = 0;     // 1: run the kernel instances that keep per-phase cycle counters
     // device tables
     int16_t *d_tab = nullptr;     // [7][N] int16: perm, inv_perm, offA, offW1, offY1, offW2, offY2
     // host tables

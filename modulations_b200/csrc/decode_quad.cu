@@ -51,6 +51,7 @@ struct QuadArgs {
     double *LeA, *LeB;
     double siso_sf;
     int vec_ab, vec_wy;   // 8-byte loads of (A,B) / (W,Y) pairs are legal for this codec + stride
+    int timed;            // development: add this launch's per-phase cycles to g_phase_cycles
     // workspace
     double2 *Le1, *Le2, *Y;
 };
@@ -733,7 +734,8 @@ quad_kernel(const QuadArgs A)
     }
     if (tid == 0) {
         ph[5] = clock64() - t_start;
-        for (int i = 0; i < 6; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)ph[i]);
+        if (A.timed)
+            for (int i = 0; i < 6; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)ph[i]);
     }
     if (!SISO_ONLY && A.counters) {
         // one atomic per warp and counter at kernel end
@@ -799,12 +801,10 @@ int quad_configure(Codec &c)
     // checkpoints are tried and the one that keeps more frames resident wins: shared memory
     // (up to 7 groups when N is small) or tensor memory (up to 4 groups: one per lane quadrant).
     const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
-    const int want_groups = getenv("B200DVB_GROUPS") ? atoi(getenv("B200DVB_GROUPS")) : kMaxGroups;
-    const int force_tmem = getenv("B200DVB_TMEM") ? atoi(getenv("B200DVB_TMEM")) : -1;
+    const int want_groups = kMaxGroups;
     QuadGeom best{};
     best.frames = 0;
     for (int tm = 0; tm < 2; ++tm) {
-        if (force_tmem >= 0 && tm != force_tmem) continue;
         QuadGeom t = g;
         t.use_tmem = tm;
         t.tmem_cols = 32;
@@ -816,8 +816,7 @@ int quad_configure(Codec &c)
         bool ok = false;
         for (; gr >= 1 && !ok; --gr) {
             t.groups = gr;
-            const int fcap = getenv("B200DVB_FRAMES") ? atoi(getenv("B200DVB_FRAMES")) : 8 * gr;
-            for (t.frames = fcap < 8 * gr ? fcap : 8 * gr; t.frames > 8 * (gr - 1) && t.frames >= 1; --t.frames) {
+            for (t.frames = 8 * gr; t.frames > 8 * (gr - 1) && t.frames >= 1; --t.frames) {
                 t.smem_bytes = quad_smem_bytes(t);
                 if (t.smem_bytes <= cap) { ok = true; break; }
             }
@@ -826,11 +825,9 @@ int quad_configure(Codec &c)
     }
     if (best.frames < 1) return B200DVB_ENOSPEC;
     g = best;
-    const bool want_y = !getenv("B200DVB_YTMEM") || atoi(getenv("B200DVB_YTMEM"));
+    const bool want_y = true;
     {
-        const char *e = getenv("B200DVB_THREADS");
-        int t = e ? atoi(e) : kMaxCtaThreads;
-        t = (t / 32) * 32;
+        int t = kMaxCtaThreads;
         if (t < kCtaThreads * g.groups) t = kCtaThreads * g.groups;
         if (t > kMaxCtaThreads) t = kMaxCtaThreads;
         g.threads = t;
@@ -901,6 +898,7 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
     const bool even = (llr_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 7) == 0);
     A.vec_ab = even && c.vec_ab;
     A.vec_wy = even && c.vec_wy;
+    A.timed = c.opt_phase_timers;
     A.Le1 = reinterpret_cast<double2 *>(align256(ws));
     A.Le2 = A.Le1 + per; A.Y = A.Le2 + per;
     if (c.geom.use_tmem) quad_kernel<false, true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);

@@ -33,8 +33,6 @@
 #include "common.cuh"
 #include "tpf_core.cuh"
 
-#include <stdlib.h>
-
 namespace b200dvb {
 
 namespace {
@@ -906,8 +904,6 @@ int tpf_configure(Codec &c)
     TpfGeom &g = c.tpf;
     g = TpfGeom{};
     const int N = c.N;
-    const char *e = getenv("B200DVB_KERNEL");
-    if (e && e[0] == 'q') return B200DVB_OK;                   // B200DVB_KERNEL=quad forces the older kernel
     if (N < 16 || (N % 4) != 0) return B200DVB_OK;
     const int M = N / 2;
     int T = M < 64 ? M : 64;
@@ -934,8 +930,9 @@ int tpf_configure(Codec &c)
     g.off_y = take((size_t)N * 16 * sizeof(double2));
     g.off_ck = take((size_t)g.nslots * 4 * 32 * sizeof(float4));
     g.ws_per_warp = off;
-    B2_CUDA(cudaFuncSetAttribute(tpf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    B2_CUDA(cudaFuncSetAttribute(tpf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    // the device's maximum, not this codec's need: the attribute is per function and device, and codecs of several N coexist
+    B2_CUDA(cudaFuncSetAttribute(tpf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    B2_CUDA(cudaFuncSetAttribute(tpf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     g.enabled = 1;
     return B200DVB_OK;
 }
@@ -976,7 +973,7 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     A.n_llr = c.n_llr;
     // whole rows by 16-byte cp.async: pitch and base 16-byte aligned, row fits half the staging area
     A.vec4 = (c.N <= 256) && (llr_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && ((c.n_llr + 3) / 4 * 4 <= kRowFloats) &&
-             !getenv("B200DVB_NOVEC4");
+             !c.opt_no_row_staging;
     if (A.vec4) {   // the group-staged transposition needs at least two padded rows (+ the offset table) in one of the warp's areas
         const int nq = (c.n_llr + 3) / 4, pitch4 = ((nq + 6) & ~7) + 1;
         const int rec_bytes = c.tpf.mid * 2 * 16 * (int)sizeof(float4);
@@ -987,8 +984,8 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;
     A.ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    // B200DVB_TPF_TIMERS=1 (development): the instance with per-phase clock64() accounting, read by b200dvb_debug_tpf_cycles
-    const bool timed = getenv("B200DVB_TPF_TIMERS") != nullptr;
+    // B200DVB_OPT_PHASE_TIMERS (development): the instance with per-phase clock64() accounting, read by b200dvb_debug_tpf_cycles
+    const bool timed = c.opt_phase_timers != 0;
     if (timed) tpf_kernel<true><<<tpf_grid(c, B), kTpfWarps * 32, c.tpf.smem_bytes, s>>>(A);
     else       tpf_kernel<false><<<tpf_grid(c, B), kTpfWarps * 32, c.tpf.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());

@@ -176,11 +176,9 @@ int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, ui
     int fpb = 32;
     while (fpb > 1 && (size_t)fpb * (in_stride + out_stride) > 96 * 1024) fpb >>= 1;
     const size_t smem = (size_t)fpb * (in_stride + out_stride);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // a per-device attribute: set on every launch (cheap) rather than cached in a process-wide flag
+    if (smem > 48 * 1024)
         B2_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     unsigned long long lut = 0;
     for (int z = 0; z < 16; ++z) lut |= (unsigned long long)(c.circ_lut[z] & 15) << (4 * z);
     const int grid = (B + fpb - 1) / fpb;

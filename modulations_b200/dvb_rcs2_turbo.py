@@ -134,13 +134,16 @@ def _trellis_tables():
 
 
 # ---------------------------------------------------------------------------
-# device handle
+# device handle: every call into libb200dvb.so for the codec goes through this class
 # ---------------------------------------------------------------------------
 class _CodecHandle:
-    """Owns one b200dvb_codec_t plus its cached workspaces on the creating device."""
+    """Owns one b200dvb_codec_t on the device that was current at construction, plus its cached
+    workspaces (one per kind and CUDA stream, so calls on different streams never share scratch).
+    All launches run with that device current and on ITS current stream, whatever device the caller
+    has selected meanwhile."""
 
     def __init__(self, N, next_state, out_W, out_Y, perm, inv_perm, punct_u8, period, iterations,
-                 sf_inner=0.7, sf_last=1.0):
+                 sf_inner=0.7, sf_last=1.0, kernel=None):
         torch = _lib.require_cuda()
         lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -153,19 +156,81 @@ class _CodecHandle:
         _lib.check(rc, f"codec_create(N={N})")
         self.h = h
         self.N = int(N)
+        self.k_info = 2 * int(N)
         self.n_llr = int(lib.b200dvb_codec_n_llr(h))
+        self.frames_per_wave = int(lib.b200dvb_codec_frames_per_wave(h))
         self._ws = {}
+        if kernel is not None:
+            self.set_option(_lib.OPT_KERNEL, {"auto": _lib.KERNEL_AUTO, "quad": _lib.KERNEL_QUAD,
+                                              "tpf": _lib.KERNEL_TPF}[kernel])
 
-    def workspace(self, kind, B):
+    def set_option(self, option, value):
+        _lib.check(_lib.load().b200dvb_codec_set_option(self.h, int(option), int(value)), "codec_set_option")
+
+    def stream(self):
+        return _lib.torch_mod().cuda.current_stream(self.device)
+
+    def workspace(self, kind, B, stream=None):
         torch = _lib.torch_mod()
         lib = _lib.load()
         fn = lib.b200dvb_decode_workspace_bytes if kind == "decode" else lib.b200dvb_siso_workspace_bytes
         need = int(fn(self.h, int(B)))
-        cur = self._ws.get(kind)
+        key = (kind, (stream or self.stream()).cuda_stream)
+        cur = self._ws.get(key)
         if cur is None or cur.numel() < need:
             cur = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws[kind] = cur
+            self._ws[key] = cur
         return cur, need
+
+    # -- the three device operations of the codec -------------------------------------------------
+    def encode(self, info, want_circ=False):
+        """info uint8 CUDA [B, 2N] -> (coded uint8 [B, n_llr], circ uint8 [B, 2] or None)."""
+        torch = _lib.torch_mod()
+        B = info.shape[0]
+        with torch.cuda.device(self.device):
+            coded = torch.empty((B, self.n_llr), dtype=torch.uint8, device=self.device)
+            circ = torch.empty((B, 2), dtype=torch.uint8, device=self.device) if want_circ else None
+            rc = _lib.load().b200dvb_encode(self.h, B, _lib.ptr(info), _lib.ptr(coded), _lib.ptr(circ),
+                                            ctypes.c_void_p(self.stream().cuda_stream))
+        _lib.check(rc, "encode")
+        return coded, circ
+
+    def decode(self, x, bits=None, packed=None, ref=None, counters=None, stream=None, ws=None):
+        """x float32 CUDA [B, >= n_llr] (row stride in elements taken from the tensor)."""
+        torch = _lib.torch_mod()
+        B = x.shape[0]
+        st = stream or self.stream()
+        with torch.cuda.device(self.device):
+            buf, need = ws if ws is not None else self.workspace("decode", B, st)
+            stride = x.stride(0) if B > 1 else x.shape[1]     # a length-1 axis may report stride 0
+            rc = _lib.load().b200dvb_decode(self.h, B, _lib.ptr(x), stride, _lib.ptr(bits), _lib.ptr(packed),
+                                            _lib.ptr(ref), _lib.ptr(counters), _lib.ptr(buf), need,
+                                            ctypes.c_void_p(st.cuda_stream))
+        _lib.check(rc, "decode")
+
+    def siso(self, f4, d2, sf):
+        """f4: four float32 CUDA [B, N] (Lc_A, Lc_B, Lc_W, Lc_Y); d2: two float64 (La_A, La_B)."""
+        torch = _lib.torch_mod()
+        B = f4[0].shape[0]
+        with torch.cuda.device(self.device):
+            LeA = torch.empty((B, self.N), dtype=torch.float64, device=self.device)
+            LeB = torch.empty_like(LeA)
+            ws, need = self.workspace("siso", B)
+            rc = _lib.load().b200dvb_siso(self.h, B, *[_lib.ptr(t) for t in f4], *[_lib.ptr(t) for t in d2],
+                                          float(sf), _lib.ptr(LeA), _lib.ptr(LeB), _lib.ptr(ws), need,
+                                          ctypes.c_void_p(self.stream().cuda_stream))
+        _lib.check(rc, "bcjr_max_log_map")
+        return LeA, LeB
+
+    def mc_generate_bpsk(self, B, noise_var, seed, frame_offset, info, coded, llr):
+        """Monte-Carlo source (b200dvb_mc_generate_bpsk): Philox info bits -> encode -> BPSK + AWGN -> LLR, written
+        into caller-owned CUDA buffers info uint8 [>=B, 2N], coded uint8 [>=B, n_llr], llr float32 [>=B, n_llr]."""
+        torch = _lib.torch_mod()
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b200dvb_mc_generate_bpsk(self.h, int(B), float(noise_var), int(seed), int(frame_offset),
+                                                      _lib.ptr(info), _lib.ptr(coded), _lib.ptr(llr),
+                                                      ctypes.c_void_p(self.stream().cuda_stream))
+        _lib.check(rc, "mc_generate_bpsk")
 
     def __del__(self):
         try:
@@ -180,7 +245,8 @@ _siso_handles = {}
 
 
 def _siso_handle(N, next_st, out_W, out_Y):
-    key = (int(N), np.asarray(next_st).tobytes(), np.asarray(out_W).tobytes(), np.asarray(out_Y).tobytes())
+    dev = _lib.require_cuda().cuda.current_device()
+    key = (dev, int(N), np.asarray(next_st).tobytes(), np.asarray(out_W).tobytes(), np.asarray(out_Y).tobytes())
     h = _siso_handles.get(key)
     if h is None:
         ident = np.arange(int(N), dtype=np.int32)
@@ -190,10 +256,16 @@ def _siso_handle(N, next_st, out_W, out_Y):
 
 
 def _as_2d(x, N):
+    """[N'] or [B, N'] -> [B, N]; like the reference's loops (``for k in range(N)``) only the first N
+    entries of each row are read."""
     torch = _lib.torch_mod()
-    if isinstance(x, torch.Tensor):
-        return x.reshape(-1, N)
-    return np.asarray(x).reshape(-1, N)
+    if not isinstance(x, torch.Tensor):
+        x = np.asarray(x)
+    if x.ndim == 1:
+        x = x[None, :]
+    if x.shape[-1] < N:
+        raise IndexError(f"SISO input has {x.shape[-1]} entries per frame, N = {N}")
+    return x[..., :N]
 
 
 def bcjr_max_log_map(Lc_A, Lc_B, Lc_W, Lc_Y, La_A, La_B, next_st, out_W, out_Y, prev_st, prev_inp,
@@ -205,25 +277,21 @@ def bcjr_max_log_map(Lc_A, Lc_B, Lc_W, Lc_Y, La_A, La_B, next_st, out_W, out_Y, 
     Bit-exact with the reference's arithmetic (float64 branch-metric sums rounded
     to float32, float32 recursions normalised by state 0, float64 extrinsic).
     Inputs may also be ``[B, N]`` (numpy or CUDA torch) for B independent frames.
-    ``prev_st`` / ``prev_inp`` are accepted for signature parity; the kernel derives
-    the reverse trellis from ``next_st``.
+
+    Narrower than the reference in three documented ways: (1) ``prev_st`` / ``prev_inp`` are accepted
+    for signature parity but not read — the kernel derives the reverse trellis from ``next_st``; (2) only
+    the committed 16-state trellis (``_trellis_tables()``) has a kernel specialisation, any other table
+    raises ``ValueError`` (B200DVB_ENOSPEC) instead of being emulated; (3) N must be a multiple of 4 in
+    [8, 2048] (every N of the reference's table is).
     """
     torch = _lib.require_cuda()
-    lib = _lib.load()
     N = int(N)
     h = _siso_handle(N, next_st, out_W, out_Y)
     is_torch = isinstance(Lc_A, torch.Tensor)
     single = (not is_torch and np.asarray(Lc_A).ndim == 1) or (is_torch and Lc_A.dim() == 1)
     f = [_lib.to_device(_as_2d(x, N), torch.float32, h.device) for x in (Lc_A, Lc_B, Lc_W, Lc_Y)]
     d = [_lib.to_device(_as_2d(x, N), torch.float64, h.device) for x in (La_A, La_B)]
-    B = f[0].shape[0]
-    LeA = torch.empty((B, N), dtype=torch.float64, device=h.device)
-    LeB = torch.empty_like(LeA)
-    ws, need = h.workspace("siso", B)
-    rc = lib.b200dvb_siso(h.h, B, *[_lib.ptr(t) for t in f], *[_lib.ptr(t) for t in d],
-                          float(scaling_factor), _lib.ptr(LeA), _lib.ptr(LeB), _lib.ptr(ws), need,
-                          _lib.stream_ptr())
-    _lib.check(rc, "bcjr_max_log_map")
+    LeA, LeB = h.siso(f, d, scaling_factor)
     if is_torch:
         return (LeA[0], LeB[0]) if single else (LeA, LeB)
     a, b = LeA.cpu().numpy(), LeB.cpu().numpy()
@@ -242,6 +310,13 @@ def bcjr_decode_circular(*args):
         return bcjr_max_log_map(*args[:6], t["next_state"], t["out_W"], t["out_Y"], t["prev_state"],
                                 t["prev_input"], N, args[6])
     raise TypeError("bcjr_decode_circular takes 13 or 7 positional arguments")
+
+
+def bcjr_decode(*args):
+    """Historic name imported by the reference's ``d_test.py:9`` (revisions 12-15 10:39 … 12-16 11:00 of
+    ``dvb_rcs2_turbo.py``; 7 arguments ``(6 LLR arrays, scaling)``).  Served by the
+    committed arithmetic like the other aliases."""
+    return bcjr_decode_circular(*args)
 
 
 def max_log_map_decode(*args):
@@ -278,14 +353,16 @@ def bijective_interleaver(N):
 
 
 class DVBRCS2_Turbo:
-    def __init__(self, N_couples, code_rate, iterations=8, perm=None):
+    def __init__(self, N_couples, code_rate, iterations=8, perm=None, kernel=None):
         """``perm`` (extension, NOT reference behaviour): a user-supplied interleaver table of length N
         replacing the committed one, whose formula is not a permutation (BER ~ 0.2 at every
         SNR).  With a bijective ``perm`` the same kernels decode properly; results are then compared with
-        the oracle given the same table, and reported as a labelled non-parity run."""
+        the oracle given the same table, and reported as a labelled non-parity run.
+        ``kernel`` (development / tests): "auto" (default), "quad" or "tpf" forces one decode kernel."""
         self.N = N_couples
         self.k_info = N_couples * 2
-        self.iterations = iterations
+        self._iterations = iterations
+        self._kernel = kernel
         self.punct = PUNCTURE_PATTERNS[code_rate]               # KeyError for unknown rates (:292)
         if self.N not in INTERLEAVER_PARAMS:                    # :295-296
             raise ValueError(f"Block size {self.N} not in standard tables.")
@@ -300,7 +377,18 @@ class DVBRCS2_Turbo:
             setattr(self, k, v)
         self._calc_coded_size()
         self._punct_u8 = np.array([self.punct[k] for k in ('W1', 'Y1', 'W2', 'Y2')], np.uint8)
-        self._handle = None
+        self._handles = {}
+        self._e2e = None
+
+    @property
+    def iterations(self):
+        """Read on every decode like the reference's attribute (:493): assigning a new value takes effect
+        on the next call (the device handle is rebuilt for it)."""
+        return self._iterations
+
+    @iterations.setter
+    def iterations(self, value):
+        self._iterations = int(value)
 
     # -- tables -------------------------------------------------------------
     def _init_interleaver(self):
@@ -320,11 +408,15 @@ class DVBRCS2_Turbo:
 
     @property
     def handle(self):
-        if self._handle is None:
-            self._handle = _CodecHandle(self.N, self.next_state, self.out_W, self.out_Y, self.perm,
-                                        self.inv_perm, self._punct_u8, self.punct['period'],
-                                        self.iterations)
-        return self._handle
+        """The device handle for (current CUDA device, current ``iterations``)."""
+        torch = _lib.require_cuda()
+        key = (torch.cuda.current_device(), int(self._iterations))
+        h = self._handles.get(key)
+        if h is None:
+            h = _CodecHandle(self.N, self.next_state, self.out_W, self.out_Y, self.perm, self.inv_perm,
+                             self._punct_u8, self.punct['period'], self._iterations, kernel=self._kernel)
+            self._handles[key] = h
+        return h
 
     @property
     def n_llr(self):
@@ -338,12 +430,7 @@ class DVBRCS2_Turbo:
         h = self.handle
         is_torch = isinstance(bits, torch.Tensor)
         info = _lib.to_device(bits, torch.uint8, h.device).reshape(-1, self.k_info)
-        B = info.shape[0]
-        coded = torch.empty((B, h.n_llr), dtype=torch.uint8, device=h.device)
-        circ = torch.empty((B, 2), dtype=torch.uint8, device=h.device) if return_circ else None
-        rc = _lib.load().b200dvb_encode(h.h, B, _lib.ptr(info), _lib.ptr(coded), _lib.ptr(circ),
-                                        _lib.stream_ptr())
-        _lib.check(rc, "encode")
+        coded, circ = h.encode(info, return_circ)
         if not is_torch:
             coded = coded.cpu().numpy()
             circ = circ.cpu().numpy() if return_circ else None
@@ -360,69 +447,89 @@ class DVBRCS2_Turbo:
     def decode_batch(self, llr, ref_bits=None, counters=None, out="bits"):
         """llr [B, >= n_llr] float32 (numpy or CUDA torch) -> hard decisions.
 
-        out="bits": int32 [B, 2N] (reference layout); "packed": uint32 [B, ceil(2N/32)];
-        "none": nothing (error counting only).  ``ref_bits`` uint8 [B, 2N] and
-        ``counters`` (CUDA uint64/int64 tensor [4]) enable in-kernel error counting:
-        counters += {bit errors, frame errors, frames, info bits}.
+        out="bits": int32 [B, 2N] (reference layout); "packed": uint32 [B, ceil(2N/32)], bit i of a frame at
+        word i//32, bit i%32; "none": nothing (error counting only).  ``ref_bits`` (anything reshapeable to
+        uint8 [B, 2N]) and ``counters`` (CUDA int64/uint64 tensor, >= 4 elements) enable in-kernel error
+        counting: counters += {bit errors, frame errors, frames, info bits}.
         """
         torch = _lib.require_cuda()
         h = self.handle
+        if out not in ("bits", "packed", "none"):
+            raise ValueError('out must be "bits", "packed" or "none"')
         is_torch = isinstance(llr, torch.Tensor)
         x = _lib.to_device(llr, torch.float32, h.device)
         if x.dim() == 1:
             x = x[None, :]
-        if x.shape[1] < h.n_llr:
-            raise IndexError(f"llr has {x.shape[1]} values per frame, the depuncturer needs {h.n_llr}")
+        if x.dim() != 2 or x.shape[1] < h.n_llr:
+            raise IndexError(f"llr has {x.shape[-1]} values per frame, the depuncturer needs {h.n_llr}")
+        if x.stride(1) != 1:
+            x = x.contiguous()
         B = x.shape[0]
         bits = packed = None
         if out == "bits":
             bits = torch.empty((B, self.k_info), dtype=torch.int32, device=h.device)
         elif out == "packed":
             packed = torch.empty((B, (self.k_info + 31) // 32), dtype=torch.int32, device=h.device)
-        ref = _lib.to_device(ref_bits, torch.uint8, h.device) if ref_bits is not None else None
+        ref = None
+        if ref_bits is not None:
+            ref = _lib.to_device(ref_bits, torch.uint8, h.device)
+            if ref.numel() != B * self.k_info:
+                raise ValueError(f"ref_bits holds {ref.numel()} bits, the batch has {B} x {self.k_info}")
+            ref = ref.reshape(B, self.k_info)
         if counters is not None and not (isinstance(counters, torch.Tensor) and counters.is_cuda
-                                         and counters.element_size() == 8 and counters.numel() >= 4):
-            raise ValueError("counters must be a CUDA int64/uint64 tensor with 4 elements")
-        ws, need = h.workspace("decode", B)
-        stride = x.stride(0) if B > 1 else x.shape[1]     # a length-1 axis may report stride 0
-        rc = _lib.load().b200dvb_decode(h.h, B, _lib.ptr(x), stride, _lib.ptr(bits),
-                                        _lib.ptr(packed), _lib.ptr(ref), _lib.ptr(counters),
-                                        _lib.ptr(ws), need, _lib.stream_ptr())
-        _lib.check(rc, "decode")
+                                         and counters.dtype in (torch.int64, torch.uint64)
+                                         and counters.numel() >= 4 and counters.is_contiguous()
+                                         and counters.device == h.device):
+            raise ValueError("counters must be a contiguous CUDA int64/uint64 tensor with >= 4 elements on the codec's device")
+        h.decode(x, bits=bits, packed=packed, ref=ref, counters=counters)
         res = bits if out == "bits" else packed
         if res is not None and not is_torch:
             res = res.cpu().numpy()
         return res
 
-    def decode_batch_host(self, llr_host, out_host=None, chunk=None):
-        """End-to-end decode of HOST buffers: pinned ``llr_host`` float32 [B, n_llr] ->
-        pinned ``out_host`` int32 [B, 2N].  Chunks are pipelined over three CUDA streams
-        so the host->device copy of chunk i+1, the decode of chunk i and the
-        device->host copy of chunk i-1 overlap.  ``chunk`` defaults to one wave of the decode
-        kernel (measured best on the B200, tools/e2e_chunks.py: filling and draining the pipeline
-        costs one chunk's copies, and a whole wave leaves no SM idle).  Returns out_host (a torch
-        CPU tensor)."""
+    def decode_batch_host(self, llr_host, out_host=None, chunk=None, out="bits"):
+        """End-to-end decode of HOST buffers: pinned ``llr_host`` float32 [B, >= n_llr] -> pinned ``out_host``.
+
+        out="bits": int32 [B, 2N], the reference's layout (1 696 B per N=212 frame over PCIe);
+        out="packed": int32 words [B, ceil(2N/32)], bit i of a frame at word i//32, bit i%32 (56 B per frame:
+        the kernel's packed output copied as it is — ``unpack_bits`` expands it lazily on the host);
+        out="uint8": uint8 [B, 2N], expanded from the packed words on the device (424 B per frame).
+
+        Chunks are pipelined over three CUDA streams so the host->device copy of chunk i+1, the decode of
+        chunk i and the device->host copy of chunk i-1 overlap.  ``chunk`` defaults to one wave of the decode
+        kernel (tools/e2e_chunks.py).  The call returns after the last device->host copy has COMPLETED: the
+        returned CPU tensor can be read at once."""
         torch = _lib.require_cuda()
         h = self.handle
+        if out not in ("bits", "packed", "uint8"):
+            raise ValueError('out must be "bits", "packed" or "uint8"')
         if chunk is None:
-            chunk = max(16, int(_lib.load().b200dvb_codec_frames_per_wave(h.h)))
+            chunk = max(16, h.frames_per_wave)
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(llr_host, np.float32))
-        if x.dim() != 2 or x.shape[1] < h.n_llr:
-            raise IndexError(f"llr needs shape [B, >= {h.n_llr}]")
+        if x.dim() != 2 or x.shape[1] < h.n_llr or x.dtype != torch.float32:
+            raise IndexError(f"llr needs float32 shape [B, >= {h.n_llr}]")
         B, width = x.shape
+        wpf = (self.k_info + 31) // 32
+        oshape, odtype = {"bits": ((self.k_info,), torch.int32), "packed": ((wpf,), torch.int32),
+                          "uint8": ((self.k_info,), torch.uint8)}[out]
         if out_host is None:
-            out_host = torch.empty((B, self.k_info), dtype=torch.int32, pin_memory=True)
+            out_host = torch.empty((B,) + oshape, dtype=odtype, pin_memory=True)
+        elif tuple(out_host.shape) != (B,) + oshape or out_host.dtype != odtype:
+            raise ValueError(f"out_host must be {odtype} of shape {(B,) + oshape}")
         nstage = 3
-        if getattr(self, "_e2e", None) is None or self._e2e[0] != (chunk, width):
-            streams = [torch.cuda.Stream(device=h.device) for _ in range(nstage)]
-            din = [torch.empty((chunk, width), dtype=torch.float32, device=h.device) for _ in range(nstage)]
-            dout = [torch.empty((chunk, self.k_info), dtype=torch.int32, device=h.device) for _ in range(nstage)]
-            need = int(_lib.load().b200dvb_decode_workspace_bytes(h.h, chunk))
-            wss = [torch.empty(need, dtype=torch.uint8, device=h.device) for _ in range(nstage)]
-            self._e2e = ((chunk, width), streams, din, dout, wss, need)
-        _, streams, din, dout, wss, need = self._e2e
-        lib = _lib.load()
-        cur = torch.cuda.current_stream(h.device)
+        key = (h, chunk, width, out)
+        if self._e2e is None or self._e2e[0] != key:
+            with torch.cuda.device(h.device):
+                streams = [torch.cuda.Stream(device=h.device) for _ in range(nstage)]
+                din = [torch.empty((chunk, width), dtype=torch.float32, device=h.device) for _ in range(nstage)]
+                dout = [torch.empty((chunk,) + oshape, dtype=odtype, device=h.device) for _ in range(nstage)]
+                dpk = [torch.empty((chunk, wpf), dtype=torch.int32, device=h.device) if out == "uint8" else None
+                       for _ in range(nstage)]
+                wss = [h.workspace("decode", chunk, st) for st in streams]
+                done = [torch.cuda.Event() for _ in range(nstage)]
+            self._e2e = (key, streams, din, dout, dpk, wss, done)
+        _, streams, din, dout, dpk, wss, done = self._e2e
+        cur = h.stream()
         for st in streams:
             st.wait_stream(cur)
         for i, lo in enumerate(range(0, B, chunk)):
@@ -430,19 +537,40 @@ class DVBRCS2_Turbo:
             j = i % nstage
             with torch.cuda.stream(streams[j]):
                 din[j][:n].copy_(x[lo:lo + n], non_blocking=True)
-                rc = lib.b200dvb_decode(h.h, n, _lib.ptr(din[j]), width, _lib.ptr(dout[j]), None, None,
-                                        None, _lib.ptr(wss[j]), need,
-                                        ctypes.c_void_p(streams[j].cuda_stream))
-                _lib.check(rc, "decode")
+                if out == "bits":
+                    h.decode(din[j][:n], bits=dout[j], stream=streams[j], ws=wss[j])
+                elif out == "packed":
+                    h.decode(din[j][:n], packed=dout[j], stream=streams[j], ws=wss[j])
+                else:
+                    h.decode(din[j][:n], packed=dpk[j], stream=streams[j], ws=wss[j])
+                    _unpack_bits_device(dpk[j][:n], dout[j][:n], self.k_info)
                 out_host[lo:lo + n].copy_(dout[j][:n], non_blocking=True)
-        for st in streams:
+                done[j].record(streams[j])
+        for j, st in enumerate(streams):
             cur.wait_stream(st)
+        for ev in done:                       # the copies land in host memory: block the HOST, not only the stream
+            ev.synchronize()
         return out_host
 
     def decode(self, llr):
         """Decode one frame of LLRs (positive = bit 0) into 2N info bits, int32 (:464-537)."""
         llr = np.array(llr, dtype=np.float32)
         return self.decode_batch(llr[None, :])[0]
+
+
+def _unpack_bits_device(packed, out_u8, k_info):
+    """packed int32 [n, W] -> out_u8 uint8 [n, k_info] on the device (plain tensor ops: plumbing, not the hot path)."""
+    torch = _lib.torch_mod()
+    sh = torch.arange(32, device=packed.device, dtype=torch.int32)
+    b = (packed.unsqueeze(-1) >> sh) & 1
+    out_u8.copy_(b.reshape(packed.shape[0], -1)[:, :k_info])
+
+
+def unpack_bits(packed, k_info):
+    """Host-side expansion of ``decode_batch_host(..., out="packed")`` words into the reference's int32 [B, 2N]."""
+    a = packed.numpy() if hasattr(packed, "numpy") else np.asarray(packed)
+    b = np.unpackbits(np.ascontiguousarray(a).view(np.uint8), axis=1, bitorder="little")
+    return b[:, :k_info].astype(np.int32)
 
 
 # ---------------------------------------------------------------------------
@@ -457,24 +585,38 @@ class _Interleaver:
         return np.asarray(A)[self.perm], np.asarray(B)[self.perm]
 
 
-class _ConstituentEncoder:
-    def __init__(self, N):
+_component_handles = {}
+
+
+def _component_handle(N):
+    """Codec handle of ONE constituent code (identity interleaver, nothing punctured), per device."""
+    dev = _lib.require_cuda().cuda.current_device()
+    h = _component_handles.get((dev, int(N)))
+    if h is None:
         t = _trellis_tables()
         ident = np.arange(N, dtype=np.int32)
-        self._h = _CodecHandle(N, t["next_state"], t["out_W"], t["out_Y"], ident, ident,
-                               np.ones((4, 1), np.uint8), 1, 1)
+        h = _CodecHandle(N, t["next_state"], t["out_W"], t["out_Y"], ident, ident, np.ones((4, 1), np.uint8), 1, 1)
+        _component_handles[(dev, int(N))] = h
+    return h
+
+
+def _component_encode(N, A, B):
+    """-> (coded uint8 numpy [N, 6], circ uint8 numpy [2]) of the constituent encoder for couples (A, B)."""
+    torch = _lib.require_cuda()
+    h = _component_handle(N)
+    bits = np.stack([np.asarray(A), np.asarray(B)], axis=1).reshape(1, -1)
+    coded, circ = h.encode(_lib.to_device(bits, torch.uint8, h.device), True)
+    return coded.cpu().numpy()[0].reshape(N, 6), circ.cpu().numpy()[0]
+
+
+class _ConstituentEncoder:
+    def __init__(self, N):
         self.N = N
 
     def encode(self, A, B):
         """Tail-biting constituent encode of couples (A, B) -> (W, Y) int32[N]."""
-        torch = _lib.require_cuda()
-        bits = np.stack([np.asarray(A), np.asarray(B)], axis=1).reshape(1, -1)
-        info = _lib.to_device(bits, torch.uint8, self._h.device)
-        coded = torch.empty((1, self._h.n_llr), dtype=torch.uint8, device=self._h.device)
-        rc = _lib.load().b200dvb_encode(self._h.h, 1, _lib.ptr(info), _lib.ptr(coded), None,
-                                        _lib.stream_ptr())
-        _lib.check(rc, "encoder.encode")
-        c = coded.cpu().numpy()[0].reshape(self.N, 6).astype(np.int32)
+        c, _ = _component_encode(self.N, A, B)
+        c = c.astype(np.int32)
         return c[:, 2].copy(), c[:, 3].copy()
 
 
@@ -516,14 +658,5 @@ class DVB_RCS2_TurboCodec:
 
 def determine_circular_state(A, B):
     """Historic name: circular start state of the constituent encoder for couples (A, B)."""
-    N = len(A)
-    enc = _ConstituentEncoder(N)
-    torch = _lib.require_cuda()
-    bits = np.stack([np.asarray(A), np.asarray(B)], axis=1).reshape(1, -1)
-    info = _lib.to_device(bits, torch.uint8, enc._h.device)
-    coded = torch.empty((1, enc._h.n_llr), dtype=torch.uint8, device=enc._h.device)
-    circ = torch.empty((1, 2), dtype=torch.uint8, device=enc._h.device)
-    rc = _lib.load().b200dvb_encode(enc._h.h, 1, _lib.ptr(info), _lib.ptr(coded), _lib.ptr(circ),
-                                    _lib.stream_ptr())
-    _lib.check(rc, "determine_circular_state")
-    return int(circ.cpu().numpy()[0, 0])
+    _, circ = _component_encode(len(A), A, B)
+    return int(circ[0])

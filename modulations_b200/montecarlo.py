@@ -99,13 +99,11 @@ def run_sweep(cfg: SweepConfig, rank=0, world=1, codec=None):
             start = lo + b * bmax
             n = max(0, min(bmax, hi - start))
             if n > 0 and cfg.modulation == 'BPSK':
-                _lib.check(lib.b200dvb_mc_generate_bpsk(h.h, n, float(nv), seed, start, _lib.ptr(info),
-                                                        _lib.ptr(coded), _lib.ptr(llr), _lib.stream_ptr()), "mc")
+                h.mc_generate_bpsk(n, nv, seed, start, info, coded, llr)
                 codec.decode_batch(llr[:n], ref_bits=info[:n], counters=cnt, out="none")
             elif n > 0:
                 # encode -> map -> complex AWGN -> max-log demap with the decoder's sign (F4)
-                _lib.check(lib.b200dvb_mc_generate_bpsk(h.h, n, 1.0, seed, start, _lib.ptr(info),
-                                                        _lib.ptr(coded), _lib.ptr(llr), _lib.stream_ptr()), "mc")
+                h.mc_generate_bpsk(n, 1.0, seed, start, info, coded, llr)
                 m = gray_modem(cfg.modulation)
                 cb = coded[:n]
                 if nsym * bps != h.n_llr:

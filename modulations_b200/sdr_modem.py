@@ -70,8 +70,9 @@ class ModemHandle:
         n = b.numel() // self.bps
         out = torch.empty(n, dtype=torch.complex128 if out_complex128 else torch.complex64,
                           device=self.device)
-        rc = _lib.load().b200dvb_map(self.h, n, _lib.ptr(b), _lib.ptr(out), int(out_complex128),
-                                     _lib.stream_ptr())
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b200dvb_map(self.h, n, _lib.ptr(b), _lib.ptr(out), int(out_complex128),
+                                         _lib.stream_ptr(self.device))
         _lib.check(rc, "map")
         return out if is_torch else out.cpu().numpy()
 
@@ -88,8 +89,9 @@ class ModemHandle:
             s = _lib.to_device(symbols, symbols.dtype if f64 else torch.complex64, self.device)
         n = s.numel()
         out = torch.empty(n * self.bps, dtype=torch.uint8, device=self.device)
-        rc = _lib.load().b200dvb_hard_demod(self.h, n, _lib.ptr(s), int(f64), _lib.ptr(out),
-                                            _lib.stream_ptr())
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b200dvb_hard_demod(self.h, n, _lib.ptr(s), int(f64), _lib.ptr(out),
+                                                _lib.stream_ptr(self.device))
         _lib.check(rc, "hard_demod")
         return out if is_torch else out.cpu().numpy()
 
@@ -101,8 +103,9 @@ class ModemHandle:
                            torch.complex64, self.device).reshape(-1)
         n = s.numel()
         out = torch.empty(n * self.bps, dtype=torch.float32, device=self.device)
-        rc = _lib.load().b200dvb_demap(self.h, n, _lib.ptr(s), float(noise_var), float(scale),
-                                       _lib.ptr(out), _lib.stream_ptr())
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b200dvb_demap(self.h, n, _lib.ptr(s), float(noise_var), float(scale),
+                                           _lib.ptr(out), _lib.stream_ptr(self.device))
         _lib.check(rc, "demap")
         return out if is_torch else out.cpu().numpy()
 
@@ -111,11 +114,13 @@ _handles = {}
 
 
 def gray_modem(modulation):
-    """Cached ModemHandle over the SDRModem (Gray) constellation."""
-    h = _handles.get(modulation)
+    """Cached ModemHandle over the SDRModem (Gray) constellation, one per CUDA device (its tables live in
+    the memory of the device that was current when it was created)."""
+    key = (_lib.require_cuda().cuda.current_device(), modulation)
+    h = _handles.get(key)
     if h is None:
         h = ModemHandle(modulation, gray_constellation(modulation))
-        _handles[modulation] = h
+        _handles[key] = h
     return h
 
 

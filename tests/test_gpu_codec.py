@@ -39,11 +39,15 @@ def test_decode_matches_reference(torch_cuda, golden, case):
     assert coded.dtype == np.uint8
     assert np.array_equal(np.packbits(coded, axis=1), k[f"{tag}/coded"])          # encoder: bit-exact
     assert np.array_equal(g.encode(info[0]), o.encode(info[0]))
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    forced = turbo.DVBRCS2_Turbo(N, rate, iters, kernel="tpf") if N <= 212 else None   # small batches go to the quad kernel
     for e, llr in zip(ebn0s, llrs):
         dec = g.decode_batch(llr)
         assert dec.dtype == np.int32 and dec.shape == (nfr, 2 * N)
         ref = o.decode_batch(llr)
         assert np.array_equal(dec, ref), f"{tag} Eb/N0={e}: {np.sum(dec != ref)} bits differ"
+        if forced is not None:
+            assert np.array_equal(forced.decode_batch(llr), ref), f"{tag} Eb/N0={e}: thread-per-frame kernel differs"
         if same_host:
             assert np.array_equal(np.packbits(dec.astype(np.uint8), axis=1), k[f"{tag}/ebn0_{e}/dec"])
     assert np.array_equal(g.decode(llrs[0][0]), ref[0] if len(ebn0s) == 1 else o.decode(llrs[0][0]))

@@ -1,8 +1,6 @@
 """GPU parity tests specific to the thread-per-frame decoder kernel (decode_tpf.cu):
 both decode kernels must agree with the oracle and with each other, bit for bit, on tile
 boundaries (16 frames per warp), strided input, packed output and the in-kernel counters."""
-import os
-
 import numpy as np
 import pytest
 
@@ -20,20 +18,11 @@ def _llrs(o, N, rate, nfr, ebn0, seed):
 
 
 def _codec(N, rate, iters, kernel):
-    """kernel: 'tpf' (default selection) or 'quad' (B200DVB_KERNEL=quad at codec creation)."""
+    """kernel: 'tpf' / 'quad' force one decode kernel (B200DVB_OPT_KERNEL), 'auto' is the production choice."""
     from modulations_b200 import dvb_rcs2_turbo as turbo
-    old = os.environ.get("B200DVB_KERNEL")
-    try:
-        if kernel == "quad":
-            os.environ["B200DVB_KERNEL"] = "quad"
-        else:
-            os.environ.pop("B200DVB_KERNEL", None)
-        return turbo.DVBRCS2_Turbo(N, rate, iters)
-    finally:
-        if old is None:
-            os.environ.pop("B200DVB_KERNEL", None)
-        else:
-            os.environ["B200DVB_KERNEL"] = old
+    if kernel == "tpf" and N > 212:
+        kernel = "auto"                          # no thread-per-frame geometry for the long frames
+    return turbo.DVBRCS2_Turbo(N, rate, iters, kernel=kernel)
 
 
 @pytest.mark.parametrize("N,rate,iters", [(212, '1/3', 8), (220, '1/3', 3), (48, '1/2', 8), (64, '1/3', 2), (424, '1/3', 1)])
@@ -43,7 +32,7 @@ def test_kernels_agree_on_tile_boundaries(N, rate, iters, nfr):
     o = oracle.OracleTurbo(N, rate, iters)
     info, llr = _llrs(o, N, rate, nfr, 2.0, 99 + N + nfr)
     ref = o.decode_batch(llr)
-    for kernel in ("tpf", "quad"):
+    for kernel in ("tpf", "quad", "auto"):
         g = _codec(N, rate, iters, kernel)
         dec = g.decode_batch(llr)
         assert np.array_equal(dec, ref), f"{kernel} kernel, N={N} R={rate} B={nfr}: {np.sum(dec != ref)} bits differ"
@@ -104,13 +93,41 @@ def test_host_pipeline_matches_resident_decode(chunk):
     want = g.decode_batch(big.cuda())
     out = g.decode_batch_host(big) if chunk is None else g.decode_batch_host(big, chunk=chunk)
     assert out.dtype == torch.int32 and tuple(out.shape) == (B, 2 * N)
-    assert bool((out.cuda() == want).all())
-    ref = torch.from_numpy(o.decode_batch(llr))
-    assert bool((out[:16] == ref).all())
+    # read on the HOST straight after the call: the device->host copies must have completed (no stream-ordered
+    # access in between that could hide a missing synchronisation)
+    got = out.numpy().copy()
+    assert np.array_equal(got, want.cpu().numpy())
+    ref = o.decode_batch(llr)
+    assert np.array_equal(got[:16], ref)
 
 
-def test_timed_kernel_instance_is_bit_exact_too(monkeypatch):
-    """B200DVB_TPF_TIMERS selects the template instance with per-phase clock64() accounting
+@pytest.mark.parametrize("mode", ["packed", "uint8"])
+def test_host_pipeline_compact_outputs(mode):
+    """out="packed" copies the kernel's packed words to the host (56 B instead of 1 696 B per N=212 frame),
+    out="uint8" one byte per bit; both must carry exactly the bits of the int32 layout."""
+    import torch
+    from modulations_b200.dvb_rcs2_turbo import unpack_bits
+    N, rate, iters = 212, '1/3', 2
+    o = oracle.OracleTurbo(N, rate, iters)
+    info, llr = _llrs(o, N, rate, 16, 2.0, 12)
+    g = _codec(N, rate, iters, "auto")
+    B = 20000
+    big = torch.from_numpy(llr).repeat((B + 15) // 16, 1)[:B].contiguous().pin_memory()
+    ref = np.tile(o.decode_batch(llr), ((B + 15) // 16, 1))[:B]
+    out = g.decode_batch_host(big, out=mode)
+    got = out.numpy().copy()
+    if mode == "packed":
+        assert out.dtype == torch.int32 and tuple(out.shape) == (B, (2 * N + 31) // 32)
+        got = unpack_bits(got, 2 * N)
+    else:
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (B, 2 * N)
+    assert np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        g.decode_batch_host(big, out_host=torch.empty((B, 2 * N), dtype=torch.int32), out=mode)
+
+
+def test_timed_kernel_instance_is_bit_exact_too():
+    """B200DVB_OPT_PHASE_TIMERS selects the template instance with per-phase clock64() accounting
     (tools/tpf_perf.py); it must decode exactly like the production instance and fill the counters."""
     from modulations_b200 import _lib
     N, rate, iters, nfr = 212, '1/3', 2, 33
@@ -124,8 +141,8 @@ def test_timed_kernel_instance_is_bit_exact_too(monkeypatch):
     assert np.array_equal(g.decode_batch(llr), ref)
     _lib.check(lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1), "read")
     assert ph[7] == 0, "the production instance keeps no phase counters"
-    monkeypatch.setenv("B200DVB_TPF_TIMERS", "1")
+    g.handle.set_option(_lib.OPT_PHASE_TIMERS, 1)
     assert np.array_equal(g.decode_batch(llr), ref)
-    monkeypatch.delenv("B200DVB_TPF_TIMERS")
+    g.handle.set_option(_lib.OPT_PHASE_TIMERS, 0)
     _lib.check(lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1), "read")
     assert ph[7] > 0 and abs(ph[:7].sum() - ph[7]) <= 0.05 * ph[7]

@@ -44,10 +44,8 @@ def turbo_rate(c):
 
 if "lat" in which:
     print("# decode latency vs batch, N=212 R=1/3 8 it: resident (device tensors, CUDA events) and decode()/decode_batch on numpy (wall)")
-    for kern in ("tpf", "quad"):
-        if kern == "quad": os.environ["B200DVB_KERNEL"] = "quad"
-        else: os.environ.pop("B200DVB_KERNEL", None)
-        c = turbo.DVBRCS2_Turbo(212, '1/3', 8)
+    for kern in ("tpf", "quad", "auto"):
+        c = turbo.DVBRCS2_Turbo(212, '1/3', 8, kernel=kern)
         for B in (1, 16, 256, 4096, 65536):
             info, llr = gen(c, max(B, 16))
             llr = llr[:B].contiguous()
@@ -58,7 +56,6 @@ if "lat" in which:
             for _ in range(5):
                 t0 = time.perf_counter(); c.decode_batch(xh); t.append(time.perf_counter() - t0)
             print(f"{kern:5s} B={B:6d}: resident {best*1e3:9.1f} us (median {med*1e3:9.1f})  = {B/best/1e3:8.3f} Mframes/s | numpy in/out wall {min(t)*1e6:9.1f} us")
-    os.environ.pop("B200DVB_KERNEL", None)
 
 if "long" in which:
     print("# long frames (table N), 8 it, resident, B sized to ~4 waves; % of the 64 ACS/clk/SM roofline at 1965 MHz")

@@ -17,7 +17,7 @@ def timeit(fn, n=3):
 cfgs = [(212, '1/3', int(sys.argv[1]) if len(sys.argv) > 1 else 262144)]
 if len(sys.argv) > 2: cfgs.append((48, '1/3', 1 << 20))
 for (N, rate, B) in cfgs:
-    c = turbo.DVBRCS2_Turbo(N, rate, 8)
+    c = turbo.DVBRCS2_Turbo(N, rate, 8, kernel='tpf')
     h = c.handle
     lib = _lib.load()
     info = torch.empty((B, 2 * N), dtype=torch.uint8, device="cuda")
@@ -37,9 +37,9 @@ for (N, rate, B) in cfgs:
           f"{fps*acs/1e12:.2f} TACS/s = {fps*acs/(64*148*1.965e9)*100:.1f}% of nominal ALU roofline; "
           f"BER={cnt[0]/max(cnt[3],1):.4f} FER={cnt[1]/max(cnt[2],1):.4f}")
     ph = np.zeros(8); lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
-    os.environ["B200DVB_TPF_TIMERS"] = "1"        # the instance of the kernel with per-phase clock64() accounting
+    h.set_option(_lib.OPT_PHASE_TIMERS, 1)        # the instance of the kernel with per-phase clock64() accounting
     c.decode_batch(llr, ref_bits=ref, counters=counters, out=outm); torch.cuda.synchronize()
-    del os.environ["B200DVB_TPF_TIMERS"]
+    h.set_option(_lib.OPT_PHASE_TIMERS, 0)
     lib.b200dvb_debug_tpf_cycles(_lib.host_ptr(ph), 1)
     tot = ph[7]
     if tot > 0:

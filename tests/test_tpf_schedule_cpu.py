@@ -28,3 +28,25 @@ def test_tpf_emulator_matches_oracle(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-2000:]
     assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 20
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"),
+                    reason="needs nvcc to compile the host side of nii_core.cuh")
+def test_nii_emulator_matches_its_model(tmp_path):
+    """The non-parity "nii" mode: the kernel's arithmetic header (nii_core.cuh: merged-branch float32 records,
+    re-associated a-posteriori maxima per parity class, float32 epilogue) replayed in the kernel's lane schedule,
+    four chained SISOs with the boundary metrics carried over, against the naive model oracle/nii_model.c."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    objs = []
+    for src in ("turbo_oracle.c", "nii_model.c"):
+        o = tmp_path / (src + ".o")
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", src), "-o", str(o)], check=True)
+        objs.append(str(o))
+    emu_o = tmp_path / "nii_emu.o"
+    subprocess.run([nvcc, "-O1", "--fmad=false", "-Xcompiler", "-ffp-contract=off", "-c",
+                    os.path.join(ROOT, "tools", "nii_emulator.cu"), "-o", str(emu_o)], check=True, capture_output=True)
+    exe = tmp_path / "nii_emu"
+    subprocess.run([nvcc, "-o", str(exe), str(emu_o)] + objs, check=True, capture_output=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 20

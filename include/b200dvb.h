@@ -86,6 +86,18 @@ int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec);
 #define B200DVB_OPT_KERNEL          1
 #define B200DVB_OPT_NO_ROW_STAGING  2
 #define B200DVB_OPT_PHASE_TIMERS    3
+/* Decoder arithmetic of b200dvb_decode (NOT a development switch: an explicit, labelled choice of the caller):
+ *   B200DVB_MODE_PARITY (default)  the reference's double-pass max-log-MAP, bit-exact with
+ *                                  dvb_rcs2_turbo.py:116-281 / :464-537;
+ *   B200DVB_MODE_NII               NON-PARITY: one pass per SISO, the circular boundary initialised from the
+ *                                  previous iteration's metrics of the same constituent decoder, float32
+ *                                  extrinsics, re-associated a-posteriori maxima (csrc/nii_core.cuh; SURVEY 8(f) N2,
+ *                                  north_star "next-iteration circular-state initialisation").  Results differ from
+ *                                  the reference's in isolated bits and are judged on BER/FER; B200DVB_ENOSPEC when N
+ *                                  has no thread-per-frame geometry (N > 212).  b200dvb_siso is always parity. */
+#define B200DVB_OPT_DECODER_MODE    4
+#define B200DVB_MODE_PARITY         0
+#define B200DVB_MODE_NII            1
 int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value);
 
 /* One SISO half-iteration for B independent frames.  Replaces bcjr_max_log_map
@@ -193,6 +205,10 @@ int b200dvb_debug_phase_cycles(double *out8_h, int reset);
  * B200DVB_OPT_PHASE_TIMERS set run the instance of the kernel that keeps these counters (the
  * production instance has no clock reads); tools/tpf_perf.py shows the use. */
 int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
+
+/* Same for the non-parity "nii" kernel: {transpose-in, "in" pass incl. prep, boundary metrics + crossing, 0,
+ * out-phase windows in shared memory, out-phase windows in tensor memory, hard decision, warp total}. */
+int b200dvb_debug_nii_cycles(double *out8_h, int reset);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the
  * two warps of a lane quadrant, as the decoder uses it; *errors_h = mismatching words. */

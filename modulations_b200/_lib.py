@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200dvb.so")
 
 OK, EINVAL, ENOSPEC, ECUDA, ENOMEM, EMOD = 0, -1, -2, -3, -4, -5
-OPT_KERNEL, OPT_NO_ROW_STAGING, OPT_PHASE_TIMERS = 1, 2, 3
+OPT_KERNEL, OPT_NO_ROW_STAGING, OPT_PHASE_TIMERS, OPT_DECODER_MODE = 1, 2, 3, 4
+MODE_PARITY, MODE_NII = 0, 1
 KERNEL_AUTO, KERNEL_QUAD, KERNEL_TPF = 0, 1, 2
 MOD_IDS = {'BPSK': 0, 'QPSK': 1, '8PSK': 2, '16QAM': 3, '64QAM': 4, '256QAM': 5}
 BPS = {'BPSK': 1, 'QPSK': 2, '8PSK': 3, '16QAM': 4, '64QAM': 6, '256QAM': 8}
@@ -51,6 +52,7 @@ SIGNATURES = {
     "b200dvb_matched_filter": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_size_t, _c_void_p, _c_void_p]),
     "b200dvb_debug_phase_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_debug_tpf_cycles": (_c_int, [_c_void_p, _c_int]),
+    "b200dvb_debug_nii_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_tmem_selftest": (_c_int, [_c_void_p]),
     "b200dvb_microbench": (_c_int, [_c_void_p]),
     "b200dvb_microbench2": (_c_int, [_c_void_p]),

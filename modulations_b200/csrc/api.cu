@@ -155,6 +155,8 @@ int b200dvb_codec_create(int N, const int32_t *next_state_h, const int32_t *out_
     if (rc != B200DVB_OK) { delete h; return rc; }
     rc = tpf_configure(c);
     if (rc != B200DVB_OK) { delete h; return rc; }
+    rc = nii_configure(c);
+    if (rc != B200DVB_OK) { delete h; return rc; }
     // stream offsets (depuncture order of dvb_rcs2_turbo.py:476-487)
     c.h_tab = (int16_t *)malloc(sizeof(int16_t) * 7 * N);
     if (!c.h_tab) { delete h; return B200DVB_ENOMEM; }
@@ -247,6 +249,7 @@ static bool use_tpf(const Codec &c, int B)
 size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B)
 {
     if (!codec || B <= 0) return 0;
+    if (codec->c.opt_mode == B200DVB_MODE_NII) return nii_workspace_bytes(codec->c, B);
     return use_tpf(codec->c, B) ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
 }
 
@@ -262,6 +265,11 @@ int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value)
         return B200DVB_OK;
     case B200DVB_OPT_NO_ROW_STAGING: c.opt_no_row_staging = value != 0; return B200DVB_OK;
     case B200DVB_OPT_PHASE_TIMERS: c.opt_phase_timers = value != 0; return B200DVB_OK;
+    case B200DVB_OPT_DECODER_MODE:
+        if (value != B200DVB_MODE_PARITY && value != B200DVB_MODE_NII) return B200DVB_EINVAL;
+        if (value == B200DVB_MODE_NII && !c.nii.enabled) return B200DVB_ENOSPEC;
+        c.opt_mode = value;
+        return B200DVB_OK;
     default: return B200DVB_EINVAL;
     }
 }
@@ -273,6 +281,9 @@ int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr
 {
     if (!codec || B < 0 || !llr || (B && !workspace)) return B200DVB_EINVAL;
     if (llr_stride < codec->c.n_llr) return B200DVB_EINVAL;
+    if (codec->c.opt_mode == B200DVB_MODE_NII)
+        return nii_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
     if (use_tpf(codec->c, B))
         return tpf_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
                                  workspace, workspace_bytes, (cudaStream_t)stream);
@@ -412,6 +423,12 @@ int b200dvb_debug_tpf_cycles(double *out8_h, int reset)
 {
     if (!out8_h) return B200DVB_EINVAL;
     return tpf_read_phase_cycles(out8_h, reset);
+}
+
+int b200dvb_debug_nii_cycles(double *out8_h, int reset)
+{
+    if (!out8_h) return B200DVB_EINVAL;
+    return nii_read_phase_cycles(out8_h, reset);
 }
 
 int b200dvb_tmem_selftest(int *errors_h)

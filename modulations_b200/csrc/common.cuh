@@ -59,7 +59,7 @@ struct TpfGeom {
     int nslots;       // checkpoints per lane
     int tmem_cols;    // TMEM columns allocated per CTA (power of two >= 8 T, >= 32)
     size_t smem_bytes;
-    size_t off_l1, off_l2, off_le, off_lef, off_y, off_ck;   // byte offsets in a warp's workspace
+    size_t off_l1, off_l2, off_le, off_lef, off_y, off_ck, off_init;   // byte offsets in a warp's workspace (off_init: nii mode only)
     size_t ws_per_warp;
 };
 
@@ -68,12 +68,14 @@ struct Codec {
     double sf_inner = 0.7, sf_last = 1.0;
     QuadGeom geom{};
     TpfGeom tpf{};
+    TpfGeom nii{};                // geometry of the non-parity "nii" mode (decode_nii.cu)
     int num_sms = 0;
     int vec_ab = 0, vec_wy = 0;   // (A,B) / (W,Y) LLR pairs are adjacent and even-aligned in the stream
     // development / test switches (b200dvb_codec_set_option); all 0 in production
     int opt_kernel = 0;           // 0: automatic choice per batch, 1: quad kernel, 2: thread-per-frame kernel
     int opt_no_row_staging = 0;   // 1: thread-per-frame transposition without the cp.async row staging
     int opt_phase_timers = 0;     // 1: run the kernel instances that keep per-phase cycle counters
+    int opt_mode = 0;             // decoder arithmetic: 0 = parity (the reference's), 1 = non-parity "nii" (B200DVB_MODE_NII)
     // device tables
     int16_t *d_tab = nullptr;     // [7][N] int16: perm, inv_perm, offA, offW1, offY1, offW2, offY2
     // host tables
@@ -111,6 +113,12 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
                       void *ws, size_t ws_bytes, cudaStream_t s);
 size_t tpf_workspace_bytes(const Codec &c, int B);
 int tpf_read_phase_cycles(double *out_h, int reset);
+int nii_configure(Codec &c);
+int nii_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
+                      uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,
+                      void *ws, size_t ws_bytes, cudaStream_t s);
+size_t nii_workspace_bytes(const Codec &c, int B);
+int nii_read_phase_cycles(double *out_h, int reset);
 int read_phase_cycles(double *out_h, int reset);
 
 int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,

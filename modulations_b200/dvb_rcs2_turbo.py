@@ -143,7 +143,7 @@ class _CodecHandle:
     has selected meanwhile."""
 
     def __init__(self, N, next_state, out_W, out_Y, perm, inv_perm, punct_u8, period, iterations,
-                 sf_inner=0.7, sf_last=1.0, kernel=None):
+                 sf_inner=0.7, sf_last=1.0, kernel=None, mode=None):
         torch = _lib.require_cuda()
         lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -163,6 +163,8 @@ class _CodecHandle:
         if kernel is not None:
             self.set_option(_lib.OPT_KERNEL, {"auto": _lib.KERNEL_AUTO, "quad": _lib.KERNEL_QUAD,
                                               "tpf": _lib.KERNEL_TPF}[kernel])
+        if mode is not None:
+            self.set_option(_lib.OPT_DECODER_MODE, mode)
 
     def set_option(self, option, value):
         _lib.check(_lib.load().b200dvb_codec_set_option(self.h, int(option), int(value)), "codec_set_option")
@@ -353,12 +355,24 @@ def bijective_interleaver(N):
 
 
 class DVBRCS2_Turbo:
-    def __init__(self, N_couples, code_rate, iterations=8, perm=None, kernel=None):
+    BOUNDARIES = {"double-pass": _lib.MODE_PARITY, "nii": _lib.MODE_NII}
+
+    def __init__(self, N_couples, code_rate, iterations=8, perm=None, kernel=None, boundary="double-pass"):
         """``perm`` (extension, NOT reference behaviour): a user-supplied interleaver table of length N
         replacing the committed one, whose formula is not a permutation (BER ~ 0.2 at every
         SNR).  With a bijective ``perm`` the same kernels decode properly; results are then compared with
         the oracle given the same table, and reported as a labelled non-parity run.
-        ``kernel`` (development / tests): "auto" (default), "quad" or "tpf" forces one decode kernel."""
+        ``kernel`` (development / tests): "auto" (default), "quad" or "tpf" forces one decode kernel.
+        ``boundary`` (extension): "double-pass" (default) is the reference's decoder, bit-exact
+        (dvb_rcs2_turbo.py:162-230: every recursion runs twice around the circular trellis).  "nii" is a
+        NON-PARITY mode: one pass per SISO, alpha[0] / beta[N] initialised from the metrics the same constituent
+        decoder reached in the previous iteration, float32 extrinsics (csrc/nii_core.cuh).  Its hard decisions
+        differ from the reference's in isolated bits; it is judged on BER/FER and checked bit for bit against
+        its own model (oracle/nii_model.c).  ``decode`` / ``decode_batch`` / ``decode_batch_host`` follow it;
+        ``bcjr_max_log_map`` and the encoder are unaffected."""
+        if boundary not in self.BOUNDARIES:
+            raise ValueError(f"boundary must be one of {sorted(self.BOUNDARIES)}")
+        self.boundary = boundary
         self.N = N_couples
         self.k_info = N_couples * 2
         self._iterations = iterations
@@ -414,7 +428,8 @@ class DVBRCS2_Turbo:
         h = self._handles.get(key)
         if h is None:
             h = _CodecHandle(self.N, self.next_state, self.out_W, self.out_Y, self.perm, self.inv_perm,
-                             self._punct_u8, self.punct['period'], self._iterations, kernel=self._kernel)
+                             self._punct_u8, self.punct['period'], self._iterations, kernel=self._kernel,
+                             mode=self.BOUNDARIES[self.boundary] if self.boundary != "double-pass" else None)
             self._handles[key] = h
         return h
 

@@ -29,7 +29,7 @@ class _OracleHandle:
     """Stand-in for modulations_b200.dvb_rcs2_turbo._CodecHandle: same methods, computed by oracle/ on CPU tensors."""
 
     def __init__(self, N, next_state, out_W, out_Y, perm, inv_perm, punct_u8, period, iterations,
-                 sf_inner=0.7, sf_last=1.0, kernel=None):
+                 sf_inner=0.7, sf_last=1.0, kernel=None, mode=None):
         import torch
         from oracle import oracle
         rate = None

@@ -9,11 +9,13 @@ with 8 max-log-MAP iterations.  One "step" = one decode pass over one batch of
 synthetic frames (1 M frames per GPU, BPSK over AWGN at Eb/N0 = 2 dB, generated on
 the device).  `value` is whole-job throughput with the LLRs already resident in HBM;
 `e2e` is the same metric through `DVBRCS2_Turbo.decode_batch_host` with pinned HOST
-buffers (H2D of the LLRs and D2H of the int32 bits inside the timed region).
+buffers (H2D of the LLRs and D2H of the hard bits inside the timed region), next to
+the pinned-copy ceiling of the box measured in the same run.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §6 for how each field is derived.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,6 +32,7 @@ N_COUPLES, RATE, ITERS, EBN0_DB = 212, '1/3', 8, 2.0
 ACS_PER_FRAME = 320 * N_COUPLES * 2 * ITERS          # 1 085 440
 NOMINAL_ACS_PER_CLK_SM = 64.0                        # 1 FADD + 1 FMNMX per ACS at 128 issue slots/clk/SM
 METRIC = "turbo_info_throughput_N212_R1/3_8it"
+WORKLOAD = "DVB-RCS2 rate-1/3 turbo, N=212 couples, BPSK AWGN Eb/N0=2 dB, max-log-MAP 8 iterations (BASELINE configs[1])"
 
 
 _OUT = sys.stdout
@@ -40,6 +43,28 @@ def measured_peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         return {}
+
+
+def lib_sha256():
+    try:
+        with open(os.path.join(ROOT, "modulations_b200", "libb200dvb.so"), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()
+    except OSError:
+        return None
+
+
+def committed_ncu(sha):
+    """profiles/r02_traffic.json: per-kernel figures read out of committed `ncu --set full` captures (DRAM bytes per
+    frame, issue-slot and pipe utilisation), stamped with the sha256 of the library they were taken on.  A figure
+    from another binary is NOT reported: the caller gets None plus the reason."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception as e:
+        return None, f"profiles/r02_traffic.json unreadable ({e!r})"
+    if tr.get("lib_sha256") != sha:
+        return None, ("profiles/r02_traffic.json was captured on another build of libb200dvb.so "
+                      f"({str(tr.get('lib_sha256'))[:12]} != {str(sha)[:12]}): re-run tools/gpu_dram.sh")
+    return tr, None
 
 
 class ClockSampler:
@@ -91,32 +116,70 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(threads=None, seconds_of_cpu=20.0):
-    """The oracle (C port of the reference decoder) on the box's host cores, on a
-    bounded sample of the same workload.  Reported baseline, not the target."""
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own numba decoder when baseline/_ref travelled and numba imports, else the C port
+# ---------------------------------------------------------------------------------------------------
+def host_frames(N, rate, frames, ebn0_db, seed, modulation="BPSK"):
+    """Host-generated LLR frames with the reference's own channel model: BPSK `2y/sigma^2` clipped to +-50
+    (turbo_test_suite.py:132-161) or QPSK `+2*sqrt(2)*y/N0` per component (test.py:62-78 with the correct sign,
+    SURVEY F4).  The encoder is the oracle's (bit-exact with the reference's, tests/test_oracle_golden.py)."""
     from oracle import oracle
+    o = oracle.OracleTurbo(N, rate, ITERS)
+    rs = np.random.RandomState(seed)
+    base = min(frames, 2048)
+    info = rs.randint(0, 2, (base, 2 * N))
+    coded = o.encode_batch(info).astype(np.float64)
+    R = {'1/3': 1 / 3, '1/2': 1 / 2, '2/3': 2 / 3, '3/4': 3 / 4}[rate]
+    reps = (frames + base - 1) // base
+    tx = np.tile(1.0 - 2.0 * coded, (reps, 1))[:frames]
+    if modulation == "BPSK":
+        nv = 1.0 / (2.0 * R * 10 ** (ebn0_db / 10))
+        llr = np.clip(2.0 * (tx + np.sqrt(nv) * rs.randn(*tx.shape)) / nv, -50, 50)
+    else:                                                    # QPSK: unit-energy symbols, two bits each
+        n0 = 1.0 / (2.0 * R * 10 ** (ebn0_db / 10))          # Es/N0 = 2 R Eb/N0
+        y = tx / np.sqrt(2.0) + np.sqrt(n0 / 2.0) * rs.randn(*tx.shape)
+        llr = np.clip(2.0 * np.sqrt(2.0) * y / n0, -50, 50)
+    return np.tile(info, (reps, 1))[:frames].astype(np.uint8), llr.astype(np.float32)
+
+
+def cpu_decode(N, rate, llr, threads=None):
+    """-> (seconds, decoded uint8 [F, 2N], kind, detail).  kind "reference": the unmodified reference's
+    `DVBRCS2_Turbo.decode` (numba) on one single-threaded process per core; "port": oracle/turbo_oracle.c on
+    `threads` threads."""
+    from baseline import ref_arm
     threads = threads or os.cpu_count() or 1
-    o = oracle.OracleTurbo(N_COUPLES, RATE, ITERS)
-    rs = np.random.RandomState(7)
-    nv = 1.0 / (2.0 * (1 / 3) * 10 ** (EBN0_DB / 10))
-    base = 64
-    info = rs.randint(0, 2, (base, 2 * N_COUPLES))
-    coded = o.encode_batch(info)
-    llr = np.clip(2.0 * ((1.0 - 2.0 * coded) + np.sqrt(nv) * rs.randn(*coded.shape)) / nv, -50, 50).astype(np.float32)
-    t = time.time(); o.decode_batch(llr[:32], threads=1); per = (time.time() - t) / 32
-    frames = int(max(threads * 32, min(seconds_of_cpu / per, 40000)))
+    ok, why = ref_arm.available()
+    if ok:
+        try:
+            r = ref_arm.decode_timed(N, rate, ITERS, llr, procs=threads)
+            return r["seconds"], r["decoded"], "reference", (
+                f"/root/reference dvb_rcs2_turbo.DVBRCS2_Turbo.decode (numba, copy in baseline/_ref), {r['procs']} "
+                f"single-threaded processes, JIT warm-up excluded")
+        except Exception as e:                               # fall through to the port, and say why
+            why = repr(e)
+    from oracle import oracle
+    o = oracle.OracleTurbo(N, rate, ITERS)
+    t = time.time()
+    dec = o.decode_batch(llr, threads=threads)
+    return time.time() - t, dec.astype(np.uint8), "port", f"oracle/turbo_oracle.c on {threads} threads (reference arm unavailable: {why})"
+
+
+def cpu_baseline(threads=None, seconds_of_cpu=20.0):
+    """The reference decoder on the box's host cores over a bounded sample of the headline workload."""
+    threads = threads or os.cpu_count() or 1
+    from baseline import ref_arm
+    per = 2.9e-3 if ref_arm.available()[0] else 1.0e-3       # s per frame per core: SURVEY §6 (numba) / round-1 port
+    frames = int(max(threads * 16, min(seconds_of_cpu * threads / per / 4, 40000)))
     frames = (frames // threads) * threads
-    x = np.tile(llr, ((frames + base - 1) // base, 1))[:frames]
-    t = time.time(); o.decode_batch(x, threads=threads); dt = time.time() - t
+    _, llr = host_frames(N_COUPLES, RATE, frames, EBN0_DB, 7)
+    dt, dec, kind, detail = cpu_decode(N_COUPLES, RATE, llr, threads)
     gbps = frames * 2 * N_COUPLES / dt / 1e9
-    return {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port",
-            "sample": f"{frames} frames N=212 R=1/3 8 it, oracle/turbo_oracle.c on {threads} threads, "
-                      f"{dt:.1f} s wall ({per * 1e3:.2f} ms/frame/core)"}, dt
+    return {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": kind,
+            "sample": f"{frames} frames N=212 R=1/3 8 it in {dt:.2f} s wall = {dt * threads / frames * 1e3:.2f} ms/frame/core; {detail}"}, dt
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference
-    itself is Python + numba and cannot be compiled ahead of time) on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only)."""
     if rank != 0:
         return
     times = []
@@ -131,19 +194,20 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbit/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "DVB-RCS2 rate-1/3 turbo, N=212 couples, BPSK AWGN Eb/N0=2 dB, 8 it "
-                                   "(bounded sample per step, see cpu_baseline.sample)"},
+            "config": {"workload": WORKLOAD, "sample": "bounded sample per step, see cpu_baseline.sample"},
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=_OUT, flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from modulations_b200 import _lib
     from modulations_b200 import dvb_rcs2_turbo as turbo
+    from modulations_b200 import montecarlo
     from modulations_b200.sdr_modem import gray_modem
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
@@ -159,18 +223,15 @@ def run_ours(args, rank, world, local_rank):
     info = torch.empty((B, codec.k_info), dtype=torch.uint8, device=dev)
     coded = torch.empty((B, h.n_llr), dtype=torch.uint8, device=dev)
     llr = torch.empty((B, h.n_llr), dtype=torch.float32, device=dev)
-    _lib.check(lib.b200dvb_mc_generate_bpsk(h.h, B, nv, 20261018, rank * B, _lib.ptr(info), _lib.ptr(coded),
-                                            _lib.ptr(llr), _lib.stream_ptr()), "mc_generate")
+    h.mc_generate_bpsk(B, nv, 20261018, rank * B, info, coded, llr)
     del coded
     bits = torch.empty((B, codec.k_info), dtype=torch.int32, device=dev)
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
-    ws, need = h.workspace("decode", B)
+    ws = h.workspace("decode", B)
     stream = torch.cuda.current_stream()
-
-    def step():
-        rc = lib.b200dvb_decode(h.h, B, _lib.ptr(llr), llr.stride(0), _lib.ptr(bits), None, _lib.ptr(info),
-                                _lib.ptr(counters), _lib.ptr(ws), need, _lib.stream_ptr())
-        _lib.check(rc, "decode")
+    mp = measured_peaks()
+    hbm = mp.get("hbm_gbs", 6650.0)
+    hbm_src = "measured" if "hbm_gbs" in mp else "fallback"
 
     def barrier():
         torch.cuda.synchronize()
@@ -178,24 +239,47 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(fn, steps, warm):
+        """`steps` calls of fn bracketed by barrier + synchronize, CUDA events on the launching stream, MAX over ranks.
+        -> (total ms, per-step ms list of this rank)."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for i in range(steps):
+            fn()
+            ev[i + 1].record(stream)
+        barrier()
+        t = torch.tensor([ev[0].elapsed_time(ev[-1])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+    def time_kernel(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    # ---- headline: resident decode, one launch per step ---------------------------------------------------------
+    def step():
+        h.decode(llr, bits=bits, ref=info, counters=counters, ws=ws)
+
     for _ in range(args.warmup):
         step()
     barrier()
     counters.zero_()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clk:
-        ev[0].record(stream)
-        for i in range(args.steps):
-            step()
-            ev[i + 1].record(stream)
-        barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        total_ms, kernel_ms = timed_steps(step, args.steps, 0)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # max over ranks
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)          # the path's one real exchange (NCCL)
-    total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     frames_per_s = world * B / (ms_per_step * 1e-3)
     gbps = frames_per_s * codec.k_info / 1e9
@@ -204,62 +288,62 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (tpf_kernel, the thread-per-frame decoder; one launch per step) ----
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     clocks = clk.summary()
-    mp = measured_peaks()
     f_nom = (mp.get("sm_max_mhz") or 1965.0) * 1e6
     avg_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = B * ACS_PER_FRAME / avg_kernel_s / 1e12          # T ACS/s on this GPU
     peak = NOMINAL_ACS_PER_CLK_SM * sms * f_nom / 1e12
-    traffic = None
-    try:        # DRAM bytes of this kernel from the committed `ncu --set full` capture, scaled per frame
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = tr["tpf_bytes_per_frame"] * B
-    except Exception:
-        pass
+    sha = lib_sha256()
+    ncu, ncu_why = committed_ncu(sha)
+    tpf_ncu = (ncu or {}).get("tpf_kernel", {})
     roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "TACS/s", "frac": achieved / peak,
-            "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per launch (profiles/r01_tpf_ncu.txt: 106 200 B/frame at 65 536 "
-                            "frames, scaled to this batch); algorithmic I/O is 7 208 B/frame (LLRs in, int32 bits out, "
-                            "reference bits in). The rest is decoder scratch that does not fit the 126 MB L2 with 64 "
-                            "frames per SM in flight: the transposed channel LLRs are re-read every half-iteration "
-                            "(3 392 B x 16) and the extrinsics are written back between half-iterations; dead scratch "
-                            "lines are dropped with discard.global.L2 (was 237 KB/frame without). 11 % of HBM peak.",
-            "note": "ACS = add-compare-select of the reference algorithm (320*N per SISO, SURVEY 8d); peak = "
-                    "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at "
-                    "128 lane-ops/clk/SM on this part, profiles/r01_microbench.txt). The kernel is bound by "
-                    "instruction issue (ncu: 60 % issue-active with one warp per scheduler), not by HBM (11 % of the "
-                    "copy peak), so MEASURED_PEAKS.json has no denominator for it.",
+            "traffic": tpf_ncu["dram_bytes_per_frame"] * B if "dram_bytes_per_frame" in tpf_ncu else None,
+            "traffic_source": (f"dram__bytes_read+write of one tpf_kernel launch ({tpf_ncu.get('capture')}), per frame, "
+                               "scaled to this batch; capture taken on the library with this sha256") if tpf_ncu else ncu_why,
+            "algorithmic_io_bytes": 7208 * B,
+            "issue_active": tpf_ncu.get("smsp__issue_active_pct"), "pipe_alu": tpf_ncu.get("pipe_alu_pct"),
+            "pipe_fma": tpf_ncu.get("pipe_fma_pct"), "lib_sha256": sha,
+            "note": "MODE: F3 merged-branch (SURVEY §0 F3: the reference trellis has parallel transitions and rounding is "
+                    "monotone, so max(fl(a+g1), fl(a+g2)) == fl(a + max(g1,g2)) bit for bit; the kernel runs 32 FADD + 16 "
+                    "FMNMX + 16 FSUB per recursion step instead of the reference's 64 + 64).  ACS = add-compare-select "
+                    "of the REFERENCE algorithm (320*N per SISO, SURVEY 8d), so `achieved` is algorithmic ACS/s; peak = "
+                    "64 ACS/clk/SM x SMs x max SM clock (issue-slot bound; FADD and FMNMX each measured at 128 "
+                    "lane-ops/clk/SM on this part, profiles/r01_microbench.txt).  The kernel is bound by instruction "
+                    "issue with ONE warp per scheduler, not by HBM, so MEASURED_PEAKS.json has no denominator for it.",
             "frac_at_measured_clock": (achieved / (NOMINAL_ACS_PER_CLK_SM * sms * clocks["sm_mhz"] * 1e6 / 1e12))
             if clocks.get("sm_mhz") else None}
 
-    # ---- demapper (second half of the headline metric): HBM-bound ---------------------
-    demap = {}
+    # ---- demapper + mapper (second half of the headline metric; BASELINE configs[3]): HBM-bound ---------------------
+    demap, mapper = {}, {}
     nsym = 1 << 27
+    chunks_for_1e10 = int(np.ceil(1e10 / nsym))
     iq = (torch.randn(nsym, 2, device=dev) * 0.7).view(torch.complex64).reshape(-1)
-    for name in ("16QAM", "256QAM"):
+    demap_ncu = (ncu or {}).get("demap", {})
+    for name in ("BPSK", "QPSK", "8PSK", "16QAM", "64QAM", "256QAM"):
         m = gray_modem(name)
         out = torch.empty(nsym * m.bps, dtype=torch.float32, device=dev)
-        ts = []
-        for i in range(3 + 5):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            _lib.check(lib.b200dvb_demap(m.h, nsym, _lib.ptr(iq), 0.05, 1.0, _lib.ptr(out), _lib.stream_ptr()), "demap")
-            b.record(stream)
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(a.elapsed_time(b))
+        ms = time_kernel(lambda: _lib.check(lib.b200dvb_demap(m.h, nsym, _lib.ptr(iq), 0.05, 1.0, _lib.ptr(out),
+                                                             _lib.stream_ptr()), "demap"))
         by = nsym * (8 + 4 * m.bps)
-        gbs = by / (np.mean(ts) * 1e-3) / 1e9
-        demap[name] = {"gsym_per_s": nsym / (np.mean(ts) * 1e-3) / 1e9, "achieved_gbs": gbs,
-                       "peak_gbs": mp.get("hbm_gbs", 6650.0), "frac": gbs / mp.get("hbm_gbs", 6650.0),
-                       "peak_source": "measured" if "hbm_gbs" in mp else "fallback",
-                       "bytes_per_symbol": 8 + 4 * m.bps, "symbols": nsym,
-                       # the same figures in the roofline object's vocabulary (HBM-bound kernel); traffic = DRAM bytes of
-                       # one launch from the committed ncu capture (profiles/r01_demap_ncu.txt: 16QAM, 2^27 symbols)
-                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": mp.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                                    "frac": gbs / mp.get("hbm_gbs", 6650.0),
-                                    "traffic": (1.073748e9 + 2.094105e9) * nsym / (1 << 27) if name == "16QAM" else None}}
+        gbs = by / (ms * 1e-3) / 1e9
+        tr = demap_ncu.get(name, {}).get("dram_bytes_per_symbol")
+        demap[name] = {"gsym_per_s": nsym / (ms * 1e-3) / 1e9, "bytes_per_symbol": 8 + 4 * m.bps, "symbols": nsym,
+                       "seconds_for_1e10_symbols": ms * 1e-3 * 1e10 / nsym,
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                    "peak_source": hbm_src, "traffic": tr * nsym if tr else None}}
         del out
+        bits_in = torch.randint(0, 2, (nsym * m.bps,), dtype=torch.uint8, device=dev)
+        sy = torch.empty(nsym, dtype=torch.complex64, device=dev)
+        ms = time_kernel(lambda: _lib.check(lib.b200dvb_map(m.h, nsym, _lib.ptr(bits_in), _lib.ptr(sy), 0, _lib.stream_ptr()), "map"))
+        by = nsym * (m.bps + 8)
+        gbs = by / (ms * 1e-3) / 1e9
+        mapper[name] = {"gsym_per_s": nsym / (ms * 1e-3) / 1e9, "bytes_per_symbol": m.bps + 8,
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                     "peak_source": hbm_src, "traffic": None},
+                        "note": "one uint8 per bit in (the reference's layout), complex64 out"}
+        del bits_in, sy
     del iq
+    demap["_what"] = (f"BASELINE configs[3]: max-log LLR demap, 2^27 resident symbols per launch (larger than L2); 1e10 symbols = "
+                      f"{chunks_for_1e10} such chunks (400 GB at 256QAM exceeds HBM), seconds_for_1e10_symbols = kernel time only")
 
     # ---- waveform stage next to the mapper / demapper: HBM-bound streaming FIRs -------------
     waveform = {}
@@ -279,78 +363,197 @@ def run_ours(args, rank, world, local_rank):
                       shaped.numel(), _lib.ptr(shaped), _lib.host_ptr(taps_h), nt, sps, start, n_mf, _lib.ptr(mf),
                       _lib.stream_ptr())))
         for name, by, call in calls:
-            ts = []
-            for i in range(3 + 5):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                _lib.check(call(), name)
-                b.record(stream)
-                torch.cuda.synchronize()
-                if i >= 3:
-                    ts.append(a.elapsed_time(b))
-            gbs = by / (np.mean(ts) * 1e-3) / 1e9
-            waveform[name] = {"gsym_per_s": nsw / (np.mean(ts) * 1e-3) / 1e9, "symbols": nsw, "sps": sps, "taps": nt,
-                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": mp.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                                           "frac": gbs / mp.get("hbm_gbs", 6650.0), "traffic": None}}
+            ms = time_kernel(lambda: _lib.check(call(), name))
+            gbs = by / (ms * 1e-3) / 1e9
+            waveform[name] = {"gsym_per_s": nsw / (ms * 1e-3) / 1e9, "symbols": nsw, "sps": sps, "taps": nt,
+                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                           "frac": gbs / hbm, "peak_source": hbm_src, "traffic": None}}
         del sy, shaped, mf
     except Exception as e:                                         # never let the optional block break the headline line
         waveform = {"error": repr(e)}
 
     # ---- BASELINE configs[2]: 16QAM symbols -> soft demap -> turbo decode, device resident ---------
     Bc = min(B, 262144)
-    nsym = (h.n_llr + 3) // 4
+    nsym16 = (h.n_llr + 3) // 4
     m16 = gray_modem("16QAM")
-    cb = torch.randint(0, 2, (Bc, nsym * 4), dtype=torch.uint8, device=dev)
+    cb = torch.randint(0, 2, (Bc, nsym16 * 4), dtype=torch.uint8, device=dev)
     syms = m16.map(cb.reshape(-1))
     syms = syms + 0.1 * (torch.randn(syms.numel(), 2, device=dev).view(torch.complex64).reshape(-1))
-    llr16 = torch.empty(syms.numel() * 4, dtype=torch.float32, device=dev)
+    llr16 = torch.empty((Bc, nsym16 * 4), dtype=torch.float32, device=dev)
     cnt16 = torch.zeros(4, dtype=torch.int64, device=dev)
-    ws16, need16 = h.workspace("decode", Bc)
+    ws16 = h.workspace("decode", Bc)
 
     def chain():
         _lib.check(lib.b200dvb_demap(m16.h, syms.numel(), _lib.ptr(syms), 0.02, -1.0, _lib.ptr(llr16), _lib.stream_ptr()), "demap")
-        _lib.check(lib.b200dvb_decode(h.h, Bc, _lib.ptr(llr16), nsym * 4, None, None, _lib.ptr(info), _lib.ptr(cnt16),
-                                      _lib.ptr(ws16), need16, _lib.stream_ptr()), "decode")
-    for _ in range(2):
-        chain()
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(args.steps):
-        chain()
-    b.record(stream)
-    barrier()
-    tc = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-    chain_ms = float(tc.item()) / args.steps
+        h.decode(llr16, ref=info[:Bc], counters=cnt16, ws=ws16)
+    chain_total, _ = timed_steps(chain, args.steps, 2)
+    chain_ms = chain_total / args.steps
     chain16 = {"info_gbit_per_s": world * Bc * codec.k_info / (chain_ms * 1e-3) / 1e9, "ms_per_step": chain_ms,
-               "frames_per_gpu": Bc, "symbols_per_frame": nsym,
+               "frames_per_gpu": Bc, "symbols_per_frame": nsym16,
                "what": "BASELINE configs[2]: 16QAM max-log demap (b200dvb_demap, decoder sign fused) + 8-iteration decode, resident"}
     del cb, syms, llr16
 
-    # ---- end to end with HOST buffers ---------------------------------------------------
+    # ---- non-parity decoder mode boundary="nii" (SURVEY 8(f) N2): reported separately, never as `value` -----------
+    nii = {}
+    try:
+        cn = turbo.DVBRCS2_Turbo(N_COUPLES, RATE, ITERS, boundary="nii")
+        hn = cn.handle
+        Bn = min(B, 262144)
+        wsn = hn.workspace("decode", Bn)
+        cntn = torch.zeros(4, dtype=torch.int64, device=dev)
+        cntp = torch.zeros(4, dtype=torch.int64, device=dev)
+        wsp = h.workspace("decode", Bn)
+        t_nii, _ = timed_steps(lambda: hn.decode(llr[:Bn], ref=info[:Bn], counters=cntn, ws=wsn), args.steps, 2)
+        t_par, _ = timed_steps(lambda: h.decode(llr[:Bn], ref=info[:Bn], counters=cntp, ws=wsp), args.steps, 2)
+        a, b = cntn.cpu().numpy().astype(float), cntp.cpu().numpy().astype(float)
+        nii = {"info_gbit_per_s": world * Bn * codec.k_info / (t_nii / args.steps * 1e-3) / 1e9,
+               "speedup_over_parity_mode": t_par / t_nii, "frames_per_gpu": Bn,
+               "ber": a[0] / max(a[3], 1), "ber_parity_mode_same_frames": b[0] / max(b[3], 1),
+               "what": "NON-PARITY mode: single pass per SISO with next-iteration boundary metrics, float32 (csrc/decode_nii.cu); "
+                       "bit-exact against its own model oracle/nii_model.c (tests/test_gpu_nii.py), BER against the parity "
+                       "mode on the same frames (committed interleaver: both floor at BER~0.2, SURVEY F2; the bijective-"
+                       "interleaver comparison inside confidence intervals is tests/test_gpu_nii.py and profiles/)"}
+        del wsn, wsp
+    except Exception as e:
+        nii = {"error": repr(e)}
+
+    # ---- end to end with HOST buffers -----------------------------------------------------------------------------
     Be = min(B, args.e2e_frames)
+    wpf = (codec.k_info + 31) // 32
     hin = torch.empty((Be, h.n_llr), dtype=torch.float32, pin_memory=True)
     hin.copy_(llr[:Be])
-    hout = torch.empty((Be, codec.k_info), dtype=torch.int32, pin_memory=True)
     torch.cuda.synchronize()
-    for _ in range(2):
-        codec.decode_batch_host(hin, hout)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(args.steps):
-        codec.decode_batch_host(hin, hout)
-    b.record(stream)
-    barrier()
-    te = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_gbps = world * Be * args.steps * codec.k_info / (float(te.item()) * 1e-3) / 1e9
-    same = bool(torch.equal(hout.to(dev), bits[:Be]))
-    chunk = int(lib.b200dvb_codec_frames_per_wave(h.h))       # decode_batch_host's default: one wave of the decode kernel
+    e2e_modes = {}
+    for mode, width, dt_ in (("packed", wpf, torch.int32), ("bits", codec.k_info, torch.int32)):
+        hout = torch.empty((Be, width), dtype=dt_, pin_memory=True)
+        tot, _ = timed_steps(lambda: codec.decode_batch_host(hin, hout, out=mode), args.steps, 2)
+        val = world * Be * args.steps * codec.k_info / (tot * 1e-3) / 1e9
+        got = turbo.unpack_bits(hout.numpy(), codec.k_info) if mode == "packed" else hout.numpy()
+        same = bool(np.array_equal(got, bits[:Be].cpu().numpy()))
+        e2e_modes[mode] = {"value": val, "d2h_bytes_per_step": Be * width * 4, "matches_resident_run": same}
+        del hout
+    # pinned-copy ceiling of this box, measured in the same run: the SAME bytes, plain cudaMemcpyAsync on two streams,
+    # no kernel, all ranks at once (tools/h2d_ceiling.py is the stand-alone version)
+    ceil = {}
+    din = torch.empty((Be, h.n_llr), dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    chunk = h.frames_per_wave
+    for mode, width in (("packed", wpf), ("bits", codec.k_info)):
+        hout = torch.empty((Be, width), dtype=torch.int32, pin_memory=True)
+        dout = torch.empty((Be, width), dtype=torch.int32, device=dev)
+
+        def copies():
+            s_in.wait_stream(stream); s_out.wait_stream(stream)
+            for lo in range(0, Be, chunk):
+                hi = min(Be, lo + chunk)
+                with torch.cuda.stream(s_in):
+                    din[lo:hi].copy_(hin[lo:hi], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hout[lo:hi].copy_(dout[lo:hi], non_blocking=True)
+            stream.wait_stream(s_in); stream.wait_stream(s_out)
+        tot, _ = timed_steps(copies, args.steps, 2)
+        ms = tot / args.steps
+        ceil[mode] = {"info_gbit_per_s": world * Be * codec.k_info / (ms * 1e-3) / 1e9,
+                      "h2d_gbs_per_gpu": Be * h.n_llr * 4 / (ms * 1e-3) / 1e9,
+                      "copy_gbs_all_gpus": world * Be * (h.n_llr * 4 + width * 4) / (ms * 1e-3) / 1e9}
+        del hout, dout
+    del din
     n_chunks = (Be + chunk - 1) // chunk
+    e2e = {"value": e2e_modes["packed"]["value"], "unit": "Gbit/s", "h2d_bytes_per_step": Be * h.n_llr * 4,
+           "d2h_bytes_per_step": e2e_modes["packed"]["d2h_bytes_per_step"], "frames_per_step": Be,
+           "api": 'DVBRCS2_Turbo.decode_batch_host(out="packed"): pinned float32 LLRs in, the kernel\'s packed hard bits '
+                  "(uint32 words, 56 B per frame) out, 3-stream pipeline, one kernel wave per chunk; the call returns after "
+                  "its last device->host copy has completed",
+           "matches_resident_run": e2e_modes["packed"]["matches_resident_run"],
+           "copy_ceiling_gbit_per_s": ceil["packed"]["info_gbit_per_s"],
+           "copy_ceiling_gbs": ceil["packed"]["copy_gbs_all_gpus"],
+           "frac_of_ceiling": e2e_modes["packed"]["value"] / ceil["packed"]["info_gbit_per_s"],
+           "frac_of_resident": e2e_modes["packed"]["value"] / gbps,
+           "int32_layout": {"value": e2e_modes["bits"]["value"], "d2h_bytes_per_step": e2e_modes["bits"]["d2h_bytes_per_step"],
+                            "matches_resident_run": e2e_modes["bits"]["matches_resident_run"],
+                            "copy_ceiling_gbit_per_s": ceil["bits"]["info_gbit_per_s"],
+                            "frac_of_ceiling": e2e_modes["bits"]["value"] / ceil["bits"]["info_gbit_per_s"],
+                            "what": 'out="bits": the reference\'s int32[B, 2N] layout (1 696 B per frame device->host)'},
+           "ceiling_what": "same bytes per step as plain pinned cudaMemcpyAsync H2D + D2H on two streams, no kernel, all "
+                           "ranks concurrently, measured in this run"}
+
+    # ---- e2e_mc: the reference's actual workflow (turbo_test_suite.py:121-199): device Philox source -> encode ->
+    #      channel -> decode -> counters; 32 bytes cross PCIe per point --------------------------------------------
+    Bm = min(B, 262144)
+    cfg = montecarlo.SweepConfig(N=N_COUPLES, rate=RATE, iterations=ITERS, ebn0_db=[EBN0_DB],
+                                 frames_per_point=world * Bm * 2, batch=Bm, seed=5)
+    montecarlo.run_sweep(cfg, rank, world, codec=codec)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_mc = montecarlo.run_sweep(cfg, rank, world, codec=codec)
+    barrier()
+    tm = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    mc_gbps = args.steps * cfg.frames_per_point * codec.k_info / float(tm.item()) / 1e9
+    e2e_mc = {"value": mc_gbps, "unit": "Gbit/s", "frac_of_resident": mc_gbps / gbps,
+              "frames_per_sweep": cfg.frames_per_point, "host_bytes_per_sweep": 32,
+              "ber": res_mc["points"][0]["ber"], "fer": res_mc["points"][0]["fer"],
+              "what": "montecarlo.run_sweep wall clock (max over ranks): Philox info bits -> encode -> BPSK/AWGN -> LLR -> "
+                      "decode -> in-kernel counters -> one all_reduce; host sees 4 int64 per Eb/N0 point"}
+
+    line_extra = {}
+    if rank == 0 and world == 1:
+        # ---- single-frame latency of the reference's call shape (turbo_test_suite.py:138-164) ---------------------
+        x1 = llr[0].cpu().numpy()
+        for _ in range(5):
+            codec.decode(x1)
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter(); codec.decode(x1); ts.append(time.perf_counter() - t0)
+        lat = {"decode_single_frame_us": float(np.median(ts) * 1e6), "what": "DVBRCS2_Turbo.decode(numpy llr) wall clock, "
+               "median of 30 (H2D + one launch + D2H); batches that fit one quad-kernel wave are dispatched to it"}
+        for Bq in (1, 256, 4096, 65536):
+            xq = llr[:Bq]
+            lat[f"resident_B{Bq}_us"] = time_kernel(lambda: codec.decode_batch(xq, out="packed"), reps=5, warm=2) * 1e3
+        # ---- the reference's only runnable self-test configuration (test.py:12-14): N=752, R=1/2 -------------------
+        c752 = turbo.DVBRCS2_Turbo(752, '1/2', ITERS)
+        h752 = c752.handle
+        B752 = 4 * h752.frames_per_wave
+        i752 = torch.empty((B752, c752.k_info), dtype=torch.uint8, device=dev)
+        c752c = torch.empty((B752, h752.n_llr), dtype=torch.uint8, device=dev)
+        l752 = torch.empty((B752, h752.n_llr), dtype=torch.float32, device=dev)
+        h752.mc_generate_bpsk(B752, 1.0 / (2 * 0.5 * 10 ** 0.2), 3, 0, i752, c752c, l752)
+        cn752 = torch.zeros(4, dtype=torch.int64, device=dev)
+        ms752 = time_kernel(lambda: c752.decode_batch(l752, ref_bits=i752, counters=cn752, out="none"), reps=3, warm=2)
+        acs752 = 320 * 752 * 2 * ITERS
+        a752 = B752 * acs752 / (ms752 * 1e-3) / 1e12
+        _, l752h = host_frames(752, '1/2', 16 * (os.cpu_count() or 1), EBN0_DB, 11)
+        dt752, dec752, kind752, det752 = cpu_decode(752, '1/2', l752h)
+        g752 = c752.decode_batch(l752h)
+        n752 = {"info_gbit_per_s": B752 * c752.k_info / (ms752 * 1e-3) / 1e9, "frames": B752, "ms": ms752,
+                "roofline": {"bound": "alu", "achieved": a752, "peak": peak, "unit": "TACS/s", "frac": a752 / peak, "traffic": None},
+                "kernel": "quad_kernel (8 frames per SM: records of longer frames do not fit on chip for the thread-per-frame mapping)",
+                "cpu_baseline": {"value": len(l752h) * c752.k_info / dt752 / 1e9, "unit": "Gbit/s", "kind": kind752,
+                                 "cores": os.cpu_count(), "sample": f"{len(l752h)} frames in {dt752:.2f} s; {det752}"},
+                "matches_cpu_arm": bool(np.array_equal(g752, dec752)),
+                "what": "N=752 couples, rate 1/2, 8 iterations: the configuration of the reference's only runnable self-test (test.py:12-14)"}
+        del i752, c752c, l752
+        # ---- BASELINE configs[0]: N=48 R=1/3 QPSK over AWGN, 100 000 IDENTICAL host-generated frames through the GPU
+        #      (decode_batch_host) and through the CPU arm, both timed ------------------------------------------------
+        c48 = turbo.DVBRCS2_Turbo(48, '1/3', ITERS)
+        _, l48 = host_frames(48, '1/3', 100_000, EBN0_DB, 13, modulation="QPSK")
+        p48 = torch.from_numpy(l48).pin_memory()
+        o48 = torch.empty((len(l48), c48.k_info), dtype=torch.int32, pin_memory=True)
+        for _ in range(2):
+            c48.decode_batch_host(p48, o48)
+        t0 = time.perf_counter()
+        c48.decode_batch_host(p48, o48)
+        gpu_s = time.perf_counter() - t0
+        dt48, dec48, kind48, det48 = cpu_decode(48, '1/3', l48)
+        cfg0 = {"frames": len(l48), "gpu_seconds": gpu_s, "gpu_info_gbit_per_s": len(l48) * 96 / gpu_s / 1e9,
+                "cpu_seconds": dt48, "cpu_info_gbit_per_s": len(l48) * 96 / dt48 / 1e9, "cpu_kind": kind48, "cpu_detail": det48,
+                "cpu_cores": os.cpu_count(), "speedup_e2e": dt48 / gpu_s,
+                "outputs_identical": bool(np.array_equal(o48.numpy().astype(np.uint8), dec48)),
+                "what": "BASELINE configs[0]: N=48 R=1/3 turbo, QPSK over AWGN (test.py:62-78 LLR with the correct sign), 8 iterations; "
+                        "GPU = DVBRCS2_Turbo.decode_batch_host wall clock (pinned host LLRs -> int32 bits on the host)"}
+        line_extra = {"latency": lat, "n752_r12": n752, "config0_n48_qpsk": cfg0}
 
     if rank == 0:
         base = cpu_baseline()[0] if world == 1 else None     # rank 0, N=1 only (tier contract)
@@ -360,26 +563,23 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": gbps, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "DVB-RCS2 rate-1/3 turbo, N=212 couples, BPSK AWGN Eb/N0=2 dB, "
-                                   f"{B} frames per GPU, max-log-MAP 8 iterations (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "frames_per_gpu": B, "mframes_per_s": frames_per_s / 1e6,
                        "cache": "inputs larger than L2 (5.09 GB of LLRs per step)",
                        "output": "int32[B,2N] bits + in-kernel error counters",
                        "parallelism": f"frames sharded over {world} GPU(s); one NCCL all-reduce of int64[4] counters"},
             "roofline": roof, "cpu_baseline": base,
-            "e2e": {"value": e2e_gbps, "unit": "Gbit/s", "h2d_bytes_per_step": Be * h.n_llr * 4,
-                    "d2h_bytes_per_step": Be * codec.k_info * 4, "frames_per_step": Be,
-                    "api": "DVBRCS2_Turbo.decode_batch_host (pinned host in/out, 3-stream pipeline, one kernel wave per chunk)",
-                    "matches_resident_run": same},
+            "e2e": e2e, "e2e_mc": e2e_mc,
             "gpu_launches": args.steps, "gpu_launches_e2e": args.steps * n_chunks,
             "clocks": clocks,
             "counters": {"bit_errors": int(cnt[0]), "frame_errors": int(cnt[1]), "frames": int(cnt[2]),
                          "bits": int(cnt[3]), "note": "BER~0.2/FER=1 is the reference's behaviour (non-bijective "
                                                      "interleaver, SURVEY F2); parity is bit-exactness, not BER"},
-            "demap": demap, "waveform": waveform, "chain_16qam": chain16,
+            "demap": demap, "mapper": mapper, "waveform": waveform, "chain_16qam": chain16, "nii_mode": nii,
             "microbench_lane_ops_per_clk_sm": {k: float(v) for k, v in zip(
                 ("fadd", "fmnmx", "acs_mix", "shfl", "dadd", "f2f", "fadd_x2", "clock_mhz"), mb)},
         }
+        line.update(line_extra)
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

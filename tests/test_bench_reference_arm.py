@@ -1,6 +1,7 @@
 """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): prints ONE JSON line with the
-contract's keys on rank 0, nothing on the other ranks, and needs no GPU.  Runs the oracle port on the host cores,
-which is one of the two places outside tests/ allowed to execute oracle/ (DESIGN.md section 6)."""
+contract's keys on rank 0, nothing on the other ranks, and needs no GPU.  It times the reference's own numba decoder
+(baseline/_ref, staged by __graft_entry__.build(): kind "reference") when that is present and numba imports, else the
+oracle port on the host cores (kind "port") — one of the two places outside tests/ allowed to execute oracle/."""
 import json
 import os
 import subprocess
@@ -25,7 +26,9 @@ def test_reference_arm_line_on_rank0():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True and d["gpu_launches"] == 0
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "N=212" in cb["sample"]
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "dvb_rcs2_turbo.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port"), cb
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "N=212" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -29,38 +29,43 @@ __global__ void encode_kernel(int B, int N, int n_llr, int fpb, int in_stride, i
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned char *s_in = sm;                               // [fpb][in_stride]
     unsigned char *s_out = sm + (size_t)fpb * in_stride;    // [fpb][out_stride]
+    int16_t *s_tab = reinterpret_cast<int16_t *>(s_out + (size_t)fpb * out_stride);   // [7][N]: the walkers' tables
     const int f0 = blockIdx.x * fpb;
     const int nf = min(fpb, B - f0);
     const int k2 = 2 * N;
+    for (int i = threadIdx.x; i < 7 * N; i += blockDim.x) s_tab[i] = tab[i];
     // stage info bits (byte granular: rows of 2N bytes need not be 16-byte aligned)
     for (int i = threadIdx.x; i < nf * k2; i += blockDim.x) {
         const int f = i / k2, j = i - f * k2;
         s_in[f * in_stride + j] = info[(size_t)(f0 + f) * k2 + j] & 1;
     }
     __syncthreads();
-    if (threadIdx.x < nf) {
-        const unsigned char *in = s_in + threadIdx.x * in_stride;
-        unsigned char *out = s_out + threadIdx.x * out_stride;
-        const int16_t *perm = tab, *offA = tab + 2 * N;
-        for (int e = 0; e < 2; ++e) {
-            const int16_t *oW = tab + (3 + 2 * e) * N, *oY = tab + (4 + 2 * e) * N;
-            int st = 0;                                     // zero-state response (:408-412)
-            for (int i = 0; i < N; ++i) {
-                const int j = e ? perm[i] : i;
-                st = trellis_next(st, in[2 * j] ^ in[2 * j + 1]);
-            }
-            st = (int)((lut >> (4 * st)) & 15ull);          // circular start state (:416-417)
-            if (circ) circ[(size_t)(f0 + threadIdx.x) * 2 + e] = (uint8_t)st;
-            for (int i = 0; i < N; ++i) {                   // :423-427
-                const int j = e ? perm[i] : i;
-                const int a = in[2 * j], b = in[2 * j + 1], ab = a ^ b;
-                const int s0 = st & 1, s1 = (st >> 1) & 1, s2 = (st >> 2) & 1;
-                if (e == 0) { const int oa = offA[i]; out[oa] = a; out[oa + 1] = b; }
-                const int ow = oW[i], oy = oY[i];
-                if (ow >= 0) out[ow] = ab ^ s0 ^ s1 ^ s2;   // :355
-                if (oy >= 0) out[oy] = ab ^ s1;             // :359
-                st = trellis_next(st, ab);
-            }
+    // Two walkers per frame, one per constituent encoder (they only share the read-only info row): the walk is a
+    // serial chain of shared-memory loads, so the kernel's speed is the number of chains in flight per SM.
+    if (threadIdx.x < 2 * nf) {
+        const int fr = threadIdx.x >> 1, e = threadIdx.x & 1;
+        const unsigned char *in = s_in + fr * in_stride;
+        unsigned char *out = s_out + fr * out_stride;
+        const int16_t *perm = s_tab, *offA = s_tab + 2 * N;
+        const int16_t *oW = s_tab + (3 + 2 * e) * N, *oY = s_tab + (4 + 2 * e) * N;
+        int st = 0;                                         // zero-state response (:408-412)
+#pragma unroll 4
+        for (int i = 0; i < N; ++i) {
+            const int j = e ? perm[i] : i;
+            st = trellis_next(st, in[2 * j] ^ in[2 * j + 1]);
+        }
+        st = (int)((lut >> (4 * st)) & 15ull);              // circular start state (:416-417)
+        if (circ) circ[(size_t)(f0 + fr) * 2 + e] = (uint8_t)st;
+#pragma unroll 4
+        for (int i = 0; i < N; ++i) {                       // :423-427
+            const int j = e ? perm[i] : i;
+            const int a = in[2 * j], b = in[2 * j + 1], ab = a ^ b;
+            const int s0 = st & 1, s1 = (st >> 1) & 1, s2 = (st >> 2) & 1;
+            if (e == 0) { const int oa = offA[i]; out[oa] = a; out[oa + 1] = b; }
+            const int ow = oW[i], oy = oY[i];
+            if (ow >= 0) out[ow] = ab ^ s0 ^ s1 ^ s2;       // :355
+            if (oy >= 0) out[oy] = ab ^ s1;                 // :359
+            st = trellis_next(st, ab);
         }
     }
     __syncthreads();
@@ -175,7 +180,7 @@ int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, ui
     const int in_stride = odd_words(2 * c.N), out_stride = odd_words(c.n_llr);
     int fpb = 32;
     while (fpb > 1 && (size_t)fpb * (in_stride + out_stride) > 96 * 1024) fpb >>= 1;
-    const size_t smem = (size_t)fpb * (in_stride + out_stride);
+    const size_t smem = (size_t)fpb * (in_stride + out_stride) + (size_t)7 * c.N * sizeof(int16_t);
     // a per-device attribute: set on every launch (cheap) rather than cached in a process-wide flag
     if (smem > 48 * 1024)
         B2_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -177,6 +177,96 @@ matched_filter_kernel(size_t n, const float2 *__restrict__ x, const __grid_const
     }
 }
 
+
+// ---- matched filter, four CONSECUTIVE outputs per thread (the default path) ---------------------------------------
+// profiles/r01_mf_ncu.txt: with one LDS.64 per tap and output the tap loop reads 392 B of shared memory per output
+// (49 taps) against 72 B of HBM: the LSU data pipe, not HBM, was the wall (80 % busy, 55 % of the copy bandwidth).
+// Consecutive outputs of one phase row read consecutive staged positions, so a thread that owns outputs 4 tid .. 4 tid+3
+// needs, per row, a window of (taps per row + 3) entries for 4 x (taps per row) MACs: 10 loads instead of 28 at 49
+// taps / sps 8 — 160 B per output.  To keep those loads conflict-free each phase row is staged in FOUR interleaved
+// sub-rows, position q at [q mod 4][q div 4]: entry e of every thread's window then sits at [(b+e) mod 4][(b+e) div 4
+// + tid], consecutive 8-byte words across the warp.  The host tabulates, per phase row p, the first staged position
+// base[p] its taps touch and the row's taps in position order (zero padded to QMAX).
+constexpr int kMf4Threads = 256;
+constexpr int kMf4Tile = 4 * kMf4Threads;
+constexpr int kMf4MaxSps = 32;
+struct FirRows {
+    float h[kMf4MaxSps * 8];        // [phase row][position within the row's window], QMAX <= 8
+    int base[kMf4MaxSps];
+};
+__device__ __forceinline__ int mf4_idx(int pos, int q4) { return (pos & 3) * q4 + (pos >> 2); }
+
+template <int QMAX>
+__global__ void __launch_bounds__(kMf4Threads, 3)
+matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirRows T, int sps,
+                       long long start, size_t n_out, float2 *__restrict__ out, int pitch, int q4, int r0, int span)
+{
+    extern __shared__ float2 xs[];                                  // [sps][4][q4] (+ pad), see above
+    const bool even = (kMf4Threads % sps) == 0;
+    const bool fast = even && (sps % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    for (size_t m0 = (size_t)blockIdx.x * kMf4Tile; m0 < n_out; m0 += (size_t)gridDim.x * kMf4Tile) {
+        const long long base = start + (long long)m0 * sps - r0;    // staged position 0 of phase 0 <-> sample `base`
+        // span (host): every staged position a window can touch, INCLUDING the entries that only meet zero-padded taps
+        // (0 x stale shared memory could be 0 x NaN)
+        __syncthreads();                                            // previous tile fully consumed
+        if (fast && base >= 0 && (size_t)(base + span + 1) <= n) {
+            const float2 *xb = x + base;
+            const int ph = (2 * threadIdx.x) % sps, step = 2 * kMf4Threads / sps;
+            const int pos0 = (2 * threadIdx.x) / sps;
+            constexpr int kIt = 6;                                  // 16-byte loads in flight per thread and pass
+            for (int r = 2 * threadIdx.x, pos = pos0; r < span; r += kIt * 2 * kMf4Threads, pos += kIt * step) {
+                float4 buf[kIt];
+#pragma unroll
+                for (int u = 0; u < kIt; ++u)
+                    if (r + u * 2 * kMf4Threads < span) buf[u] = __ldg(reinterpret_cast<const float4 *>(xb + r + u * 2 * kMf4Threads));
+#pragma unroll
+                for (int u = 0; u < kIt; ++u)
+                    if (r + u * 2 * kMf4Threads < span) {
+                        const int o = mf4_idx(pos + u * step, q4);
+                        xs[ph * pitch + o] = make_float2(buf[u].x, buf[u].y);
+                        xs[(ph + 1) * pitch + o] = make_float2(buf[u].z, buf[u].w);
+                    }
+            }
+        } else {
+            for (int r = threadIdx.x; r < span; r += kMf4Threads) {
+                const long long i = base + r;
+                xs[(r % sps) * pitch + mf4_idx(r / sps, q4)] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        float2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+        const float2 *xt = xs + threadIdx.x;
+        for (int p = 0; p < sps; ++p) {
+            const int b = T.base[p];
+            const float2 *row = xt + p * pitch;
+            float2 w[QMAX + 3];
+#pragma unroll
+            for (int e = 0; e < QMAX + 3; ++e) w[e] = row[mf4_idx(b + e, q4)];
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                const float hh = T.h[p * 8 + q];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[j].x = fmaf(w[q + j].x, hh, acc[j].x);
+                    acc[j].y = fmaf(w[q + j].y, hh, acc[j].y);
+                }
+            }
+        }
+        const size_t m = m0 + 4 * (size_t)threadIdx.x;
+        if (m + 4 <= n_out && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         :: "l"(out + m), "f"(acc[0].x), "f"(acc[0].y), "f"(acc[1].x), "f"(acc[1].y),
+                            "f"(acc[2].x), "f"(acc[2].y), "f"(acc[3].x), "f"(acc[3].y) : "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (m + j < n_out) out[m + j] = acc[j];
+        }
+    }
+}
+
 int fill_taps(FirTaps &T, const double *taps_h, int ntaps)
 {
     if (ntaps < 1 || ntaps > kMaxFirTaps) return B200DVB_EINVAL;
@@ -219,6 +309,52 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
                           size_t n_out, void *out, cudaStream_t s)
 {
     if (n_out == 0) return B200DVB_OK;
+    if (ntaps < 1 || ntaps > kMaxFirTaps) return B200DVB_EINVAL;
+    int dev = 0, sms = 148;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int Qrow = (ntaps + sps - 1) / sps;                       // taps per phase row (at most)
+    if (Qrow <= 8 && sps <= kMf4MaxSps) {
+        // four consecutive outputs per thread (matched_filter4_kernel)
+        const long long lo4 = start - (ntaps - 1);
+        const int r04 = ntaps - 1 + (int)(((lo4 % sps) + sps) % sps);
+        FirRows R;
+        for (int i = 0; i < kMf4MaxSps * 8; ++i) R.h[i] = 0.f;
+        for (int p = 0; p < kMf4MaxSps; ++p) R.base[p] = 0;
+        int omax = 0;
+        for (int p = 0; p < sps; ++p) {
+            int bmin = 1 << 30;
+            for (int t = 0; t < ntaps; ++t)
+                if ((r04 - t) % sps == p && (r04 - t) / sps < bmin) bmin = (r04 - t) / sps;
+            if (bmin == (1 << 30)) bmin = 0;                        // a row without taps (ntaps < sps)
+            R.base[p] = bmin;
+            for (int t = 0; t < ntaps; ++t)
+                if ((r04 - t) % sps == p) R.h[p * 8 + (r04 - t) / sps - bmin] = (float)taps_h[t];
+            if (bmin > omax) omax = bmin;
+        }
+        const int qmax = Qrow <= 4 ? 4 : Qrow <= 6 ? 6 : Qrow <= 7 ? 7 : 8;
+        int q4 = (kMf4Tile + omax + qmax + 3 + 3) / 4 + 1;          // entries per sub-row: the tile + the windows' reach
+        while ((q4 & 15) != 2) ++q4;                                // sub-row pitch = 2 and row pitch = 4 (mod 8) words: the
+        const int pitch4 = 4 * q4 + 4;                              // staging stores of a warp spread over all banks
+        const size_t smem4 = (size_t)sps * pitch4 * sizeof(float2);
+        const int span4 = (omax + kMf4Tile - 1 + qmax + 3) * sps;   // all positions any window reads, in samples
+        if (smem4 <= 200 * 1024) {
+            size_t blocks = (n_out + kMf4Tile - 1) / kMf4Tile;
+            if (blocks > (size_t)sms * 6) blocks = (size_t)sms * 6;
+            const float2 *xi = reinterpret_cast<const float2 *>(x);
+            float2 *oo = reinterpret_cast<float2 *>(out);
+#define B2_MF4(Q)                                                                                                      \
+            do {                                                                                                       \
+                if (smem4 > 48 * 1024)                                                                                 \
+                    B2_CUDA(cudaFuncSetAttribute(matched_filter4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+                matched_filter4_kernel<Q><<<(unsigned)blocks, kMf4Threads, smem4, s>>>(n, xi, R, sps, start, n_out, oo, pitch4, q4, r04, span4); \
+            } while (0)
+            if (qmax == 4) B2_MF4(4); else if (qmax == 6) B2_MF4(6); else if (qmax == 7) B2_MF4(7); else B2_MF4(8);
+#undef B2_MF4
+            B2_CUDA(cudaGetLastError());
+            return B200DVB_OK;
+        }
+    }
     FirTaps T;
     if (int rc = fill_taps(T, taps_h, ntaps)) return rc;
     // staged positions per phase: 256 outputs + the taps' reach + the rounding of the origin; odd pitch (in 8-byte
@@ -229,9 +365,6 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
     for (int t = 0; t < ntaps; ++t) T.off[t] = ((r0 - t) % sps) * pitch + (r0 - t) / sps;
     const size_t smem = (size_t)sps * pitch * sizeof(float2);
     if (smem > 200 * 1024) return B200DVB_EINVAL;
-    int dev = 0, sms = 148;
-    B2_CUDA(cudaGetDevice(&dev));
-    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (smem > 48 * 1024)
         B2_CUDA(cudaFuncSetAttribute(matched_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t blocks = (n_out + kMfTile - 1) / kMfTile;

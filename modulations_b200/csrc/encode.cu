@@ -34,10 +34,38 @@ __global__ void encode_kernel(int B, int N, int n_llr, int fpb, int in_stride, i
     const int nf = min(fpb, B - f0);
     const int k2 = 2 * N;
     for (int i = threadIdx.x; i < 7 * N; i += blockDim.x) s_tab[i] = tab[i];
-    // stage info bits (byte granular: rows of 2N bytes need not be 16-byte aligned)
-    for (int i = threadIdx.x; i < nf * k2; i += blockDim.x) {
-        const int f = i / k2, j = i - f * k2;
-        s_in[f * in_stride + j] = info[(size_t)(f0 + f) * k2 + j] & 1;
+    // stage info bits.  The block's frames are ONE contiguous run of nf * 2N bytes in global memory: it is read with
+    // 16-byte loads (several in flight per thread; a byte loop with a division per element spent 55 % of this kernel
+    // waiting on one load at a time, profiles/r02_encode_ncu.txt) and scattered into the padded rows byte by byte.
+    {
+        const uint8_t *g = info + (size_t)f0 * k2;
+        const int total = nf * k2;
+        const int nv = (reinterpret_cast<uintptr_t>(g) & 15) == 0 ? total / 16 : 0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(g);
+#pragma unroll 4
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            const uint4 d = __ldg(src + v);
+            const unsigned w[4] = {d.x, d.y, d.z, d.w};
+            int f = (v * 16) / k2, j = v * 16 - f * k2;
+            if ((k2 & 3) == 0) {                            // rows are whole words (N is a multiple of 4 everywhere in the table)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    *reinterpret_cast<unsigned *>(s_in + f * in_stride + j) = w[t] & 0x01010101u;
+                    j += 4;
+                    if (j == k2) { j = 0; ++f; }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    s_in[f * in_stride + j] = (w[t >> 2] >> (8 * (t & 3))) & 1u;
+                    if (++j == k2) { j = 0; ++f; }
+                }
+            }
+        }
+        for (int i = nv * 16 + threadIdx.x; i < total; i += blockDim.x) {
+            const int f = i / k2, j = i - f * k2;
+            s_in[f * in_stride + j] = g[i] & 1;
+        }
     }
     __syncthreads();
     // Two walkers per frame, one per constituent encoder (they only share the read-only info row): the walk is a
@@ -69,9 +97,34 @@ __global__ void encode_kernel(int B, int N, int n_llr, int fpb, int in_stride, i
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nf * n_llr; i += blockDim.x) {
-        const int f = i / n_llr, j = i - f * n_llr;
-        coded[(size_t)(f0 + f) * n_llr + j] = s_out[f * out_stride + j];
+    {   // the block's code words are one contiguous run of nf * n_llr bytes: gathered 16 at a time, 16-byte stores
+        uint8_t *g = coded + (size_t)f0 * n_llr;
+        const int total = nf * n_llr;
+        const int nv = (reinterpret_cast<uintptr_t>(g) & 15) == 0 ? total / 16 : 0;
+        uint4 *dst = reinterpret_cast<uint4 *>(g);
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            int f = (v * 16) / n_llr, j = v * 16 - f * n_llr;
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+            if ((n_llr & 3) == 0) {                         // whole words per row: four 32-bit reads
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    w[t] = *reinterpret_cast<const unsigned *>(s_out + f * out_stride + j);
+                    j += 4;
+                    if (j == n_llr) { j = 0; ++f; }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    w[t >> 2] |= (unsigned)s_out[f * out_stride + j] << (8 * (t & 3));
+                    if (++j == n_llr) { j = 0; ++f; }
+                }
+            }
+            dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        for (int i = nv * 16 + threadIdx.x; i < total; i += blockDim.x) {
+            const int f = i / n_llr, j = i - f * n_llr;
+            g[i] = s_out[f * out_stride + j];
+        }
     }
 }
 

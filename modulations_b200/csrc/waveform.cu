@@ -20,6 +20,8 @@
 // parity is a stated tolerance (tests/test_gpu_waveform.py), not bit-exactness.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace b200dvb {
 
 namespace {
@@ -178,79 +180,96 @@ matched_filter_kernel(size_t n, const float2 *__restrict__ x, const __grid_const
 }
 
 
-// ---- matched filter, four CONSECUTIVE outputs per thread (the default path) ---------------------------------------
-// profiles/r01_mf_ncu.txt: with one LDS.64 per tap and output the tap loop reads 392 B of shared memory per output
+// ---- matched filter, four CONSECUTIVE outputs per thread, phase PAIRS, double-buffered (the default path) ---------
+// profiles/r01_mf_ncu.txt: with one LDS.64 per tap and output the tap loop read 392 B of shared memory per output
 // (49 taps) against 72 B of HBM: the LSU data pipe, not HBM, was the wall (80 % busy, 55 % of the copy bandwidth).
-// Consecutive outputs of one phase row read consecutive staged positions, so a thread that owns outputs 4 tid .. 4 tid+3
-// needs, per row, a window of (taps per row + 3) entries for 4 x (taps per row) MACs: 10 loads instead of 28 at 49
-// taps / sps 8 — 160 B per output.  To keep those loads conflict-free each phase row is staged in FOUR interleaved
-// sub-rows, position q at [q mod 4][q div 4]: entry e of every thread's window then sits at [(b+e) mod 4][(b+e) div 4
-// + tid], consecutive 8-byte words across the warp.  The host tabulates, per phase row p, the first staged position
-// base[p] its taps touch and the row's taps in position order (zero padded to QMAX).
-constexpr int kMf4Threads = 256;
+//  * Consecutive outputs of one phase row read consecutive staged positions, so a thread that owns outputs
+//    4 tid .. 4 tid + 3 needs, per row, a window of (taps per row + 3) entries for 4 x (taps per row) MACs.
+//  * Two neighbouring samples (phases 2 pp, 2 pp + 1 of one position) are staged as ONE 16-byte entry: a 16-byte
+//    global read lands with one 16-byte shared-memory write, and one LDS.128 of the tap loop serves two phase rows:
+//    11 LDS.128 per phase pair and four outputs at 49 taps / sps 8 — 176 B per output instead of 392.
+//  * To keep the window loads conflict-free each pair row is staged in FOUR interleaved sub-rows, position q at
+//    [q mod 4][q div 4]: entry e of every thread's window then sits at [(b+e) mod 4][(b+e) div 4 + tid], consecutive
+//    16-byte words across the warp.
+//  * Staging is asynchronous (cp.async, 16 bytes) into the other of two buffers while the current tile is computed:
+//    the load-then-compute phases of a block no longer alternate, HBM requests stay in flight all the time.
+// The host tabulates, per pair row, the first staged position its taps touch and both phases' taps in position order
+// (zero padded to QW).  Even sps only; odd sps takes matched_filter_kernel.
+constexpr int kMf4Threads = 128;
 constexpr int kMf4Tile = 4 * kMf4Threads;
-constexpr int kMf4MaxSps = 32;
+constexpr int kMf4MaxPairs = 16;    // sps <= 32
+constexpr int kMf4MaxQ = 9;
 struct FirRows {
-    float h[kMf4MaxSps * 8];        // [phase row][position within the row's window], QMAX <= 8
-    int base[kMf4MaxSps];
+    float h[kMf4MaxPairs][2][kMf4MaxQ + 1];   // [pair row][phase in pair][position within the pair row's window]
+    int base[kMf4MaxPairs];
 };
 __device__ __forceinline__ int mf4_idx(int pos, int q4) { return (pos & 3) * q4 + (pos >> 2); }
 
-template <int QMAX>
+template <int QW>
 __global__ void __launch_bounds__(kMf4Threads, 3)
 matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirRows T, int sps,
                        long long start, size_t n_out, float2 *__restrict__ out, int pitch, int q4, int r0, int span)
 {
-    extern __shared__ float2 xs[];                                  // [sps][4][q4] (+ pad), see above
-    const bool even = (kMf4Threads % sps) == 0;
-    const bool fast = even && (sps % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    for (size_t m0 = (size_t)blockIdx.x * kMf4Tile; m0 < n_out; m0 += (size_t)gridDim.x * kMf4Tile) {
-        const long long base = start + (long long)m0 * sps - r0;    // staged position 0 of phase 0 <-> sample `base`
-        // span (host): every staged position a window can touch, INCLUDING the entries that only meet zero-padded taps
-        // (0 x stale shared memory could be 0 x NaN)
-        __syncthreads();                                            // previous tile fully consumed
-        if (fast && base >= 0 && (size_t)(base + span + 1) <= n) {
-            const float2 *xb = x + base;
-            const int ph = (2 * threadIdx.x) % sps, step = 2 * kMf4Threads / sps;
-            const int pos0 = (2 * threadIdx.x) / sps;
-            constexpr int kIt = 6;                                  // 16-byte loads in flight per thread and pass
-            for (int r = 2 * threadIdx.x, pos = pos0; r < span; r += kIt * 2 * kMf4Threads, pos += kIt * step) {
-                float4 buf[kIt];
-#pragma unroll
-                for (int u = 0; u < kIt; ++u)
-                    if (r + u * 2 * kMf4Threads < span) buf[u] = __ldg(reinterpret_cast<const float4 *>(xb + r + u * 2 * kMf4Threads));
-#pragma unroll
-                for (int u = 0; u < kIt; ++u)
-                    if (r + u * 2 * kMf4Threads < span) {
-                        const int o = mf4_idx(pos + u * step, q4);
-                        xs[ph * pitch + o] = make_float2(buf[u].x, buf[u].y);
-                        xs[(ph + 1) * pitch + o] = make_float2(buf[u].z, buf[u].w);
-                    }
-            }
-        } else {
-            for (int r = threadIdx.x; r < span; r += kMf4Threads) {
-                const long long i = base + r;
-                xs[(r % sps) * pitch + mf4_idx(r / sps, q4)] = (i >= 0 && (size_t)i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
-            }
+    extern __shared__ float4 xs4[];                                 // [2 buffers][sps / 2][4][q4]
+    const int npair = sps >> 1;
+    const int bufsz = npair * pitch;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const int span2 = span >> 1;                                    // 16-byte entries per tile (span is a multiple of sps)
+    auto tile_base = [&](size_t m0) { return start + (long long)m0 * sps - r0; };   // sample of staged position 0, phase 0
+    auto interior = [&](size_t m0) {
+        const long long base = tile_base(m0);
+        return aligned && base >= 0 && (size_t)(base + span) <= n && (base & 1) == 0;
+    };
+    auto stage_async = [&](size_t m0, float4 *buf) {
+        const float4 *xb = reinterpret_cast<const float4 *>(x + tile_base(m0));
+        for (int i = threadIdx.x; i < span2; i += kMf4Threads) {
+            const int pp = i % npair, pos = i / npair;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(buf + pp * pitch + mf4_idx(pos, q4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(xb + i) : "memory");
         }
+    };
+    auto stage_sync = [&](size_t m0, float4 *buf) {
+        const long long base = tile_base(m0);
+        for (int i = threadIdx.x; i < span2; i += kMf4Threads) {
+            const int pp = i % npair, pos = i / npair;
+            const long long i0 = base + 2 * (long long)i, i1 = i0 + 1;
+            const float2 a = (i0 >= 0 && (size_t)i0 < n) ? __ldg(x + i0) : make_float2(0.f, 0.f);
+            const float2 c = (i1 >= 0 && (size_t)i1 < n) ? __ldg(x + i1) : make_float2(0.f, 0.f);
+            buf[pp * pitch + mf4_idx(pos, q4)] = make_float4(a.x, a.y, c.x, c.y);
+        }
+    };
+    const size_t stride = (size_t)gridDim.x * kMf4Tile;
+    size_t m0 = (size_t)blockIdx.x * kMf4Tile;
+    int cur = 0;
+    if (m0 < n_out && interior(m0)) stage_async(m0, xs4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; m0 < n_out; m0 += stride, cur ^= 1) {
+        float4 *buf = xs4 + cur * bufsz;
+        const size_t m1 = m0 + stride;
+        if (m1 < n_out && interior(m1)) stage_async(m1, xs4 + (cur ^ 1) * bufsz);   // the other buffer was released by the
+        asm volatile("cp.async.commit_group;" ::: "memory");                         // barrier at the end of the last tile
+        if (!interior(m0)) stage_sync(m0, buf);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         float2 acc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
-        const float2 *xt = xs + threadIdx.x;
-        for (int p = 0; p < sps; ++p) {
-            const int b = T.base[p];
-            const float2 *row = xt + p * pitch;
-            float2 w[QMAX + 3];
+        const float4 *xt = buf + threadIdx.x;
+        for (int pp = 0; pp < npair; ++pp) {
+            const int b = T.base[pp];
+            const float4 *row = xt + pp * pitch;
+            float4 w[QW + 3];
 #pragma unroll
-            for (int e = 0; e < QMAX + 3; ++e) w[e] = row[mf4_idx(b + e, q4)];
+            for (int e = 0; e < QW + 3; ++e) w[e] = row[mf4_idx(b + e, q4)];
 #pragma unroll
-            for (int q = 0; q < QMAX; ++q) {
-                const float hh = T.h[p * 8 + q];
+            for (int q = 0; q < QW; ++q) {
+                const float ha = T.h[pp][0][q], hb = T.h[pp][1][q];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    acc[j].x = fmaf(w[q + j].x, hh, acc[j].x);
-                    acc[j].y = fmaf(w[q + j].y, hh, acc[j].y);
+                    acc[j].x = fmaf(w[q + j].x, ha, acc[j].x);
+                    acc[j].y = fmaf(w[q + j].y, ha, acc[j].y);
+                    acc[j].x = fmaf(w[q + j].z, hb, acc[j].x);
+                    acc[j].y = fmaf(w[q + j].w, hb, acc[j].y);
                 }
             }
         }
@@ -264,7 +283,9 @@ matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_cons
             for (int j = 0; j < 4; ++j)
                 if (m + j < n_out) out[m + j] = acc[j];
         }
+        __syncthreads();                                            // this tile's buffer may be refilled now
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 int fill_taps(FirTaps &T, const double *taps_h, int ntaps)
@@ -314,33 +335,37 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int Qrow = (ntaps + sps - 1) / sps;                       // taps per phase row (at most)
-    if (Qrow <= 8 && sps <= kMf4MaxSps) {
-        // four consecutive outputs per thread (matched_filter4_kernel)
+    if (Qrow + 1 <= kMf4MaxQ && (sps % 2) == 0 && sps / 2 <= kMf4MaxPairs) {
+        // four consecutive outputs per thread, phase pairs, double-buffered (matched_filter4_kernel)
         const long long lo4 = start - (ntaps - 1);
-        const int r04 = ntaps - 1 + (int)(((lo4 % sps) + sps) % sps);
+        const int r04 = ntaps - 1 + (int)(((lo4 % sps) + sps) % sps);   // staged sample index of the first output's tap 0
         FirRows R;
-        for (int i = 0; i < kMf4MaxSps * 8; ++i) R.h[i] = 0.f;
-        for (int p = 0; p < kMf4MaxSps; ++p) R.base[p] = 0;
-        int omax = 0;
-        for (int p = 0; p < sps; ++p) {
-            int bmin = 1 << 30;
+        memset(&R, 0, sizeof R);
+        int omax = 0, qw = 1;
+        for (int pp = 0; pp < sps / 2; ++pp) {
+            int bmin = 1 << 30, bmax = -1;
             for (int t = 0; t < ntaps; ++t)
-                if ((r04 - t) % sps == p && (r04 - t) / sps < bmin) bmin = (r04 - t) / sps;
-            if (bmin == (1 << 30)) bmin = 0;                        // a row without taps (ntaps < sps)
-            R.base[p] = bmin;
+                if (((r04 - t) % sps) >> 1 == pp) {
+                    const int o = (r04 - t) / sps;
+                    if (o < bmin) bmin = o;
+                    if (o > bmax) bmax = o;
+                }
+            if (bmax < 0) { bmin = 0; bmax = 0; }                   // a pair row without taps (ntaps < sps)
+            R.base[pp] = bmin;
             for (int t = 0; t < ntaps; ++t)
-                if ((r04 - t) % sps == p) R.h[p * 8 + (r04 - t) / sps - bmin] = (float)taps_h[t];
+                if (((r04 - t) % sps) >> 1 == pp) R.h[pp][(r04 - t) % sps & 1][(r04 - t) / sps - bmin] = (float)taps_h[t];
             if (bmin > omax) omax = bmin;
+            if (bmax - bmin + 1 > qw) qw = bmax - bmin + 1;
         }
-        const int qmax = Qrow <= 4 ? 4 : Qrow <= 6 ? 6 : Qrow <= 7 ? 7 : 8;
-        int q4 = (kMf4Tile + omax + qmax + 3 + 3) / 4 + 1;          // entries per sub-row: the tile + the windows' reach
-        while ((q4 & 15) != 2) ++q4;                                // sub-row pitch = 2 and row pitch = 4 (mod 8) words: the
-        const int pitch4 = 4 * q4 + 4;                              // staging stores of a warp spread over all banks
-        const size_t smem4 = (size_t)sps * pitch4 * sizeof(float2);
-        const int span4 = (omax + kMf4Tile - 1 + qmax + 3) * sps;   // all positions any window reads, in samples
+        const int qsel = qw <= 4 ? 4 : qw <= 6 ? 6 : qw <= 7 ? 7 : qw <= 8 ? 8 : 9;
+        int q4 = (kMf4Tile + omax + qsel + 3 + 3) / 4 + 1;          // entries per sub-row: the tile + the windows' reach
+        while ((q4 & 7) != 2) ++q4;                                 // sub-row pitch = 2 (mod 8) 16-byte words: a warp's cp.async
+        const int pitch4 = 4 * q4;                                  // writes (4 pairs x 8 positions) spread over all banks
+        const size_t smem4 = (size_t)2 * (sps / 2) * pitch4 * sizeof(float4);
+        const int span4 = (omax + kMf4Tile - 1 + qsel + 3) * sps;   // all positions any window reads, in samples
         if (smem4 <= 200 * 1024) {
             size_t blocks = (n_out + kMf4Tile - 1) / kMf4Tile;
-            if (blocks > (size_t)sms * 6) blocks = (size_t)sms * 6;
+            if (blocks > (size_t)sms * 3) blocks = (size_t)sms * 3; // persistent: three double-buffered blocks per SM
             const float2 *xi = reinterpret_cast<const float2 *>(x);
             float2 *oo = reinterpret_cast<float2 *>(out);
 #define B2_MF4(Q)                                                                                                      \
@@ -349,7 +374,7 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
                     B2_CUDA(cudaFuncSetAttribute(matched_filter4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
                 matched_filter4_kernel<Q><<<(unsigned)blocks, kMf4Threads, smem4, s>>>(n, xi, R, sps, start, n_out, oo, pitch4, q4, r04, span4); \
             } while (0)
-            if (qmax == 4) B2_MF4(4); else if (qmax == 6) B2_MF4(6); else if (qmax == 7) B2_MF4(7); else B2_MF4(8);
+            if (qsel == 4) B2_MF4(4); else if (qsel == 6) B2_MF4(6); else if (qsel == 7) B2_MF4(7); else if (qsel == 8) B2_MF4(8); else B2_MF4(9);
 #undef B2_MF4
             B2_CUDA(cudaGetLastError());
             return B200DVB_OK;

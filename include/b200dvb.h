@@ -210,6 +210,11 @@ int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
  * out-phase windows in shared memory, out-phase windows in tensor memory, hard decision, warp total}. */
 int b200dvb_debug_nii_cycles(double *out8_h, int reset);
 
+/* Process-wide development switches (never needed in production).
+ *   B200DVB_DBG_MF_VARIANT  matched-filter kernel: 0 = default, 1 = double-buffered cp.async staging, 2 = round-1 kernel */
+#define B200DVB_DBG_MF_VARIANT 1
+int b200dvb_debug_set_option(int option, int value);
+
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the
  * two warps of a lane quadrant, as the decoder uses it; *errors_h = mismatching words. */
 int b200dvb_tmem_selftest(int *errors_h);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200dvb_pulse_shape": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "b200dvb_matched_filter": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_size_t, _c_void_p, _c_void_p]),
     "b200dvb_debug_phase_cycles": (_c_int, [_c_void_p, _c_int]),
+    "b200dvb_debug_set_option": (_c_int, [_c_int, _c_int]),
     "b200dvb_debug_tpf_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_debug_nii_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_tmem_selftest": (_c_int, [_c_void_p]),

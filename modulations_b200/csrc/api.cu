@@ -431,6 +431,17 @@ int b200dvb_debug_nii_cycles(double *out8_h, int reset)
     return nii_read_phase_cycles(out8_h, reset);
 }
 
+int b200dvb_debug_set_option(int option, int value)
+{
+    switch (option) {
+    case B200DVB_DBG_MF_VARIANT:
+        if (value < 0 || value > 2) return B200DVB_EINVAL;
+        set_mf_variant(value);
+        return B200DVB_OK;
+    default: return B200DVB_EINVAL;
+    }
+}
+
 int b200dvb_tmem_selftest(int *errors_h)
 {
     if (!errors_h) return B200DVB_EINVAL;

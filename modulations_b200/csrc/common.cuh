@@ -140,6 +140,7 @@ int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int 
 int launch_matched_filter(size_t n, const void *x, const double *taps_h, int ntaps, int sps, long long start,
                           size_t n_out, void *out, cudaStream_t s);
 
+void set_mf_variant(int v);
 int modem_build_pwl(Modem &m);
 int run_microbench(double *results_h);
 int run_microbench2(double *results16_h);

@@ -205,12 +205,13 @@ struct FirRows {
 };
 __device__ __forceinline__ int mf4_idx(int pos, int q4) { return (pos & 3) * q4 + (pos >> 2); }
 
-template <int QW>
-__global__ void __launch_bounds__(kMf4Threads, 3)
+template <int QW, bool ASYNC>
+__global__ void __launch_bounds__(kMf4Threads, ASYNC ? 3 : 6)
 matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_constant__ FirRows T, int sps,
-                       long long start, size_t n_out, float2 *__restrict__ out, int pitch, int q4, int r0, int span)
+                       long long start, size_t n_out, float2 *__restrict__ out, int pitch, int q4, int r0, int span,
+                       int pair_shift)
 {
-    extern __shared__ float4 xs4[];                                 // [2 buffers][sps / 2][4][q4]
+    extern __shared__ float4 xs4[];                                 // [2 buffers (ASYNC) | 1][sps / 2][4][q4]
     const int npair = sps >> 1;
     const int bufsz = npair * pitch;
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -222,10 +223,31 @@ matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_cons
     };
     auto stage_async = [&](size_t m0, float4 *buf) {
         const float4 *xb = reinterpret_cast<const float4 *>(x + tile_base(m0));
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+#pragma unroll 4
         for (int i = threadIdx.x; i < span2; i += kMf4Threads) {
-            const int pp = i % npair, pos = i / npair;
-            const unsigned d = (unsigned)__cvta_generic_to_shared(buf + pp * pitch + mf4_idx(pos, q4));
+            const int pp = pair_shift >= 0 ? (i & (npair - 1)) : i % npair, pos = pair_shift >= 0 ? (i >> pair_shift) : i / npair;
+            const unsigned d = sbase + 16u * (unsigned)(pp * pitch + mf4_idx(pos, q4));
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(xb + i) : "memory");
+        }
+    };
+    // interior tile staged through registers: every 16-byte load of a thread in flight before its first store
+    auto stage_regs = [&](size_t m0, float4 *buf) {
+        const float4 *xb = reinterpret_cast<const float4 *>(x + tile_base(m0));
+        constexpr int kIt = 6;
+        for (int i0 = threadIdx.x; i0 < span2; i0 += kIt * kMf4Threads) {
+            float4 v[kIt];
+#pragma unroll
+            for (int u = 0; u < kIt; ++u)
+                if (i0 + u * kMf4Threads < span2) v[u] = __ldg(xb + i0 + u * kMf4Threads);
+#pragma unroll
+            for (int u = 0; u < kIt; ++u) {
+                const int i = i0 + u * kMf4Threads;
+                if (i < span2) {
+                    const int pp = pair_shift >= 0 ? (i & (npair - 1)) : i % npair, pos = pair_shift >= 0 ? (i >> pair_shift) : i / npair;
+                    buf[pp * pitch + mf4_idx(pos, q4)] = v[u];
+                }
+            }
         }
     };
     auto stage_sync = [&](size_t m0, float4 *buf) {
@@ -241,15 +263,21 @@ matched_filter4_kernel(size_t n, const float2 *__restrict__ x, const __grid_cons
     const size_t stride = (size_t)gridDim.x * kMf4Tile;
     size_t m0 = (size_t)blockIdx.x * kMf4Tile;
     int cur = 0;
-    if (m0 < n_out && interior(m0)) stage_async(m0, xs4);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (; m0 < n_out; m0 += stride, cur ^= 1) {
+    if (ASYNC) {
+        if (m0 < n_out && interior(m0)) stage_async(m0, xs4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (; m0 < n_out; m0 += stride, cur ^= ASYNC ? 1 : 0) {
         float4 *buf = xs4 + cur * bufsz;
-        const size_t m1 = m0 + stride;
-        if (m1 < n_out && interior(m1)) stage_async(m1, xs4 + (cur ^ 1) * bufsz);   // the other buffer was released by the
-        asm volatile("cp.async.commit_group;" ::: "memory");                         // barrier at the end of the last tile
-        if (!interior(m0)) stage_sync(m0, buf);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (ASYNC) {
+            const size_t m1 = m0 + stride;
+            if (m1 < n_out && interior(m1)) stage_async(m1, xs4 + (cur ^ 1) * bufsz);   // the other buffer was released by the
+            asm volatile("cp.async.commit_group;" ::: "memory");                         // barrier at the end of the last tile
+            if (!interior(m0)) stage_sync(m0, buf);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            if (interior(m0)) stage_regs(m0, buf); else stage_sync(m0, buf);
+        }
         __syncthreads();
         float2 acc[4];
 #pragma unroll
@@ -296,6 +324,11 @@ int fill_taps(FirTaps &T, const double *taps_h, int ntaps)
 }
 
 }  // namespace
+
+// development: 0 = default (four outputs per thread, phase pairs, staged through registers), 1 = the same with
+// double-buffered cp.async staging, 2 = the round-1 kernel (two strided outputs per thread)
+static int g_mf_variant = 0;
+void set_mf_variant(int v) { g_mf_variant = v; }
 
 int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int ntaps, int sps, void *out, cudaStream_t s)
 {
@@ -361,21 +394,27 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
         int q4 = (kMf4Tile + omax + qsel + 3 + 3) / 4 + 1;          // entries per sub-row: the tile + the windows' reach
         while ((q4 & 7) != 2) ++q4;                                 // sub-row pitch = 2 (mod 8) 16-byte words: a warp's cp.async
         const int pitch4 = 4 * q4;                                  // writes (4 pairs x 8 positions) spread over all banks
-        const size_t smem4 = (size_t)2 * (sps / 2) * pitch4 * sizeof(float4);
+        const bool use_async = g_mf_variant == 1;
+        const size_t smem4 = (size_t)(use_async ? 2 : 1) * (sps / 2) * pitch4 * sizeof(float4);
+        int pair_shift = -1;
+        for (int b = 0; b < 5; ++b) if ((sps / 2) == (1 << b)) pair_shift = b;
         const int span4 = (omax + kMf4Tile - 1 + qsel + 3) * sps;   // all positions any window reads, in samples
-        if (smem4 <= 200 * 1024) {
+        if (smem4 <= 200 * 1024 && g_mf_variant != 2) {
             size_t blocks = (n_out + kMf4Tile - 1) / kMf4Tile;
-            if (blocks > (size_t)sms * 3) blocks = (size_t)sms * 3; // persistent: three double-buffered blocks per SM
+            const size_t per_sm = use_async ? 3 : 6;                // persistent blocks per SM
+            if (blocks > (size_t)sms * per_sm) blocks = (size_t)sms * per_sm;
             const float2 *xi = reinterpret_cast<const float2 *>(x);
             float2 *oo = reinterpret_cast<float2 *>(out);
-#define B2_MF4(Q)                                                                                                      \
+#define B2_MF4K(Q, A)                                                                                                  \
             do {                                                                                                       \
                 if (smem4 > 48 * 1024)                                                                                 \
-                    B2_CUDA(cudaFuncSetAttribute(matched_filter4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
-                matched_filter4_kernel<Q><<<(unsigned)blocks, kMf4Threads, smem4, s>>>(n, xi, R, sps, start, n_out, oo, pitch4, q4, r04, span4); \
+                    B2_CUDA(cudaFuncSetAttribute(matched_filter4_kernel<Q, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+                matched_filter4_kernel<Q, A><<<(unsigned)blocks, kMf4Threads, smem4, s>>>(n, xi, R, sps, start, n_out, oo, pitch4, q4, r04, span4, pair_shift); \
             } while (0)
+#define B2_MF4(Q) do { if (use_async) B2_MF4K(Q, true); else B2_MF4K(Q, false); } while (0)
             if (qsel == 4) B2_MF4(4); else if (qsel == 6) B2_MF4(6); else if (qsel == 7) B2_MF4(7); else if (qsel == 8) B2_MF4(8); else B2_MF4(9);
 #undef B2_MF4
+#undef B2_MF4K
             B2_CUDA(cudaGetLastError());
             return B200DVB_OK;
         }

@@ -37,11 +37,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "once":       # ncu target: (pulse_shape
             _lib.check(call(), name)
         torch.cuda.synchronize()
     sys.exit(0)
-for name, by, call in calls:
+variants = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0]
+for var in variants:
+  lib.b200dvb_debug_set_option(1, var)
+  print(f"# matched-filter variant {var}")
+  for name, by, call in calls:
     ts = []
     for i in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); _lib.check(call(), name); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     t = min(ts[2:])
-    print(f"{name}: {t:.3f} ms  {n / t / 1e6:.1f} Gsym/s  {by / t / 1e6:.0f} GB/s")
+    print(f"{name}: {t:.3f} ms  {n / t / 1e6:.1f} Gsym/s  {by / t / 1e6:.0f} GB/s = {by / t / 1e6 / 6545.3 * 100:.1f}% of the measured copy bandwidth")

@@ -562,7 +562,7 @@ tpf_kernel(const TpfArgs A)
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((2 * N * 2 + 15) / 16) * 16;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_raw + tab_bytes);
-    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 32);
+    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 64);   // 32 B of slots + four 8-byte mbarriers
     unsigned char *stage_all = reinterpret_cast<unsigned char *>(srec_all + (size_t)kTpfWarps * g.mid * 2 * 16);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -570,6 +570,9 @@ tpf_kernel(const TpfArgs A)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < 2 * N; i += blockDim.x) tab[i] = A.tab[i];
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw + tab_bytes + 32 + 8 * warp);   // this warp's mbarrier
+    unsigned mphase = 0;
+    if (lane == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -634,16 +637,17 @@ tpf_kernel(const TpfArgs A)
                 const unsigned o2 = (unsigned short)__ldg(g_off + 3 * N + k), o3 = (unsigned short)__ldg(g_off + 4 * N + k);
                 otab[k] = make_int4((int)(oa | (op << 16)), (int)(o0 | (o1 << 16)), (int)(o2 | (o3 << 16)), 0);
             }
+            // whole rows by bulk copy (cp.async.bulk: one instruction of one lane per 5 KB row, completed on this
+            // warp's mbarrier) — the rows are the longest contiguous transfers of the kernel
             auto pull = [&](int g0) {
-                for (int r = 0; r < G; ++r) {
-                    const long long frame = frame0 + g0 + r;
-                    if (frame < A.B) {
-                        const float4 *src = reinterpret_cast<const float4 *>(A.llr + frame * A.llr_stride);
-                        float4 *dst = rowbuf + r * pitch4;
-                        for (int i = lane; i < nq; i += 32) cpa16_stream(dst + i, src + i, c.pol, c.one);
-                    }
+                if (lane == 0) {
+                    int live_rows = 0;
+                    for (int r = 0; r < G; ++r) live_rows += frame0 + g0 + r < A.B;
+                    fence_proxy_async();                            // the row buffer was read (or held records) before
+                    mbar_expect_tx(mbar, (unsigned)(live_rows * nq * 16));
+                    for (int r = 0; r < live_rows; ++r)
+                        bulk_g2s_stream(rowbuf + r * pitch4, A.llr + (frame0 + g0 + r) * A.llr_stride, (unsigned)(nq * 16), mbar, c.pol);
                 }
-                cpa_commit();
             };
             pull(0);
             if (A.ref_bits) {                                       // the hard decision will want these rows in L2
@@ -654,8 +658,8 @@ tpf_kernel(const TpfArgs A)
             }
             const float *row = reinterpret_cast<const float *>(rowbuf + fr * pitch4);
             for (int g0 = 0; g0 < kTpfFrames; g0 += G) {
-                cpa_wait<0>();
-                __syncwarp();
+                mbar_wait(mbar, mphase);
+                mphase ^= 1u;
                 const bool livef = frame0 + g0 + fr < A.B;
 #pragma unroll 4
                 for (int k0 = 0; k0 < N; k0 += KQ) {
@@ -837,7 +841,7 @@ int tpf_configure(Codec &c)
     while (g.tmem_cols < 8 * T + 4 * kW) g.tmem_cols *= 2;        // records + the window's Y
     if (g.tmem_cols > 512) return B200DVB_OK;
     const size_t tab_bytes = ((size_t)2 * N * 2 + 15) / 16 * 16;
-    g.smem_bytes = tab_bytes + 32 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
+    g.smem_bytes = tab_bytes + 64 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
     int dev = 0;
     cudaDeviceProp prop;
     B2_CUDA(cudaGetDevice(&dev));

@@ -54,6 +54,34 @@ __device__ __forceinline__ void cpa16_stream(void *dst, const void *src, unsigne
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- bulk asynchronous copies (the TMA unit's non-tensor path: cp.async.bulk, SASS UBLKCP) completed on an
+//      mbarrier.  Used where a transfer is one long contiguous run (whole LLR rows of the transposition): ONE
+//      instruction of ONE lane moves a 5 KB row, against 10 LDGSTS warp-instructions with 12 shared-memory
+//      wavefronts each --------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{   // one arrival + the number of bytes the bulk copies of this phase will deliver
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" :: "r"(mbar), "r"(parity) : "memory");
+}
+// generic-proxy accesses to a shared-memory buffer (earlier reads / writes by ld/st) ordered before the async-proxy
+// writes of the bulk copies that reuse it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, unsigned bytes, unsigned mbar, unsigned long long pol)
+{   // bytes: a multiple of 16; dst / src 16-byte aligned; read-once data: L2 evict-first
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
+}
+
 // The workspace is scratch: once a line of Y / checkpoints / old extrinsics has been consumed it
 // is dead until it is rewritten.  discard.global.L2 drops it WITHOUT a write-back, so the 160 MB of
 // scratch of the resident warps stops streaming through HBM (it was 150 KB of DRAM writes per frame).

@@ -50,7 +50,7 @@ PUNCTURE_PATTERNS = {
 def build_lib(force: bool = False) -> str:
     """Compile turbo_oracle.c -> oracle/liboracle.so (gcc, a second or two)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("turbo_oracle.c", "nii_model.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("turbo_oracle.c", "nii_model.c", "nii16_model.c", "Makefile")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"],
                               stdout=subprocess.DEVNULL)
@@ -216,6 +216,42 @@ class NiiModel(OracleTurbo):
                 rc = min(ex.map(lambda i: run(int(cuts[i]), int(cuts[i + 1])), range(threads)))
         if rc != 0:
             raise IndexError("llr shorter than the depuncturer consumes")
+        return dec
+
+    def decode(self, llr):
+        return self.decode_batch(np.asarray(llr, np.float32)[None, :])[0]
+
+
+class Nii16Model(OracleTurbo):
+    """Model of the NON-PARITY fixed-point decoder mode "nii16" (oracle/nii16_model.c).  Not the reference."""
+
+    def decode_batch(self, llr, threads=1, sf_inner_q=45, sf_last_q=64):
+        llr = np.ascontiguousarray(llr, np.float32)
+        B, n = llr.shape
+        dec = np.zeros((B, self.k_info), np.int32)
+        fn = lib().nii16_decode_batch
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 8 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_int,
+                                                                                       ctypes.c_void_p]
+
+        def run(lo, hi):
+            if hi <= lo:
+                return 0
+            return fn(int(hi - lo), self.N, self.iterations, self.next_state.ctypes.data, self.out_W.ctypes.data,
+                      self.out_Y.ctypes.data, self.prev_state.ctypes.data, self.prev_input.ctypes.data,
+                      self.perm.ctypes.data, self.inv_perm.ctypes.data, self.punct_u8.ctypes.data, self.period,
+                      int(sf_inner_q), int(sf_last_q), llr[lo:hi].ctypes.data, int(n), dec[lo:hi].ctypes.data)
+        if threads <= 1:
+            rc = run(0, B)
+        else:
+            # the model's overflow flag is a file-scope variable: worker threads only ever SET it, which is benign
+            cuts = np.linspace(0, B, threads + 1).astype(int)
+            with ThreadPoolExecutor(threads) as ex:
+                rc = min(ex.map(lambda i: run(int(cuts[i]), int(cuts[i + 1])), range(threads)))
+        if rc == -1:
+            raise IndexError("llr shorter than the depuncturer consumes")
+        if rc == -2:
+            raise OverflowError("a 16-bit quantity of the nii16 format overflowed")
         return dec
 
     def decode(self, llr):

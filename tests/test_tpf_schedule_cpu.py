@@ -50,3 +50,25 @@ def test_nii_emulator_matches_its_model(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-2000:]
     assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 20
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"),
+                    reason="needs nvcc to compile the host side of nii16_core.cuh")
+def test_nii16_emulator_matches_its_model(tmp_path):
+    """The fixed-point non-parity mode "nii16": the kernel's packed-s16x2 arithmetic header (host definitions of the DPX
+    operations) replayed in the lane schedule with two different frames per register, against the naive integer model
+    oracle/nii16_model.c (which also range-checks every 16-bit quantity), incl. saturated inputs."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    objs = []
+    for src in ("turbo_oracle.c", "nii16_model.c"):
+        o = tmp_path / (src + ".o")
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", src), "-o", str(o)], check=True)
+        objs.append(str(o))
+    emu_o = tmp_path / "nii16_emu.o"
+    subprocess.run([nvcc, "-O1", "-c", os.path.join(ROOT, "tools", "nii16_emulator.cu"), "-o", str(emu_o)],
+                   check=True, capture_output=True)
+    exe = tmp_path / "nii16_emu"
+    subprocess.run([nvcc, "-o", str(exe), str(emu_o)] + objs, check=True, capture_output=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 20

@@ -98,6 +98,12 @@ int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec);
 #define B200DVB_OPT_DECODER_MODE    4
 #define B200DVB_MODE_PARITY         0
 #define B200DVB_MODE_NII            1
+/*   B200DVB_MODE_NII16             NON-PARITY: the nii decoder in 16-bit fixed point, two frames per 32-bit register,
+ *                                  add-compare-select as one DPX instruction (VIADDMNMX.S16x2) per branch pair
+ *                                  (csrc/nii16_core.cuh states the format: LLRs in 1/4 units clamped to +-31.75,
+ *                                  extrinsics to +-63.75, scaling factors in Q6); checked bit for bit against
+ *                                  oracle/nii16_model.c */
+#define B200DVB_MODE_NII16          2
 int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value);
 
 /* One SISO half-iteration for B independent frames.  Replaces bcjr_max_log_map

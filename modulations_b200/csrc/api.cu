@@ -207,7 +207,8 @@ int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec)
 {
     if (!codec) return B200DVB_EINVAL;
     const Codec &c = codec->c;
-    if (c.tpf.enabled) return c.num_sms * kTpfWarps * kTpfFrames;
+    if (c.opt_mode == B200DVB_MODE_NII16) return c.num_sms * kTpfWarps * kTpfFrames * 2;   // two frames per lane
+    if (c.opt_mode == B200DVB_MODE_NII || c.tpf.enabled) return c.num_sms * kTpfWarps * kTpfFrames;
     return c.num_sms * c.geom.ctas_per_sm * c.geom.frames;
 }
 
@@ -249,7 +250,7 @@ static bool use_tpf(const Codec &c, int B)
 size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B)
 {
     if (!codec || B <= 0) return 0;
-    if (codec->c.opt_mode == B200DVB_MODE_NII) return nii_workspace_bytes(codec->c, B);
+    if (codec->c.opt_mode != B200DVB_MODE_PARITY) return nii_workspace_bytes(codec->c, B);
     return use_tpf(codec->c, B) ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
 }
 
@@ -266,8 +267,8 @@ int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value)
     case B200DVB_OPT_NO_ROW_STAGING: c.opt_no_row_staging = value != 0; return B200DVB_OK;
     case B200DVB_OPT_PHASE_TIMERS: c.opt_phase_timers = value != 0; return B200DVB_OK;
     case B200DVB_OPT_DECODER_MODE:
-        if (value != B200DVB_MODE_PARITY && value != B200DVB_MODE_NII) return B200DVB_EINVAL;
-        if (value == B200DVB_MODE_NII && !c.nii.enabled) return B200DVB_ENOSPEC;
+        if (value != B200DVB_MODE_PARITY && value != B200DVB_MODE_NII && value != B200DVB_MODE_NII16) return B200DVB_EINVAL;
+        if (value != B200DVB_MODE_PARITY && !c.nii.enabled) return B200DVB_ENOSPEC;
         c.opt_mode = value;
         return B200DVB_OK;
     default: return B200DVB_EINVAL;
@@ -281,7 +282,7 @@ int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr
 {
     if (!codec || B < 0 || !llr || (B && !workspace)) return B200DVB_EINVAL;
     if (llr_stride < codec->c.n_llr) return B200DVB_EINVAL;
-    if (codec->c.opt_mode == B200DVB_MODE_NII)
+    if (codec->c.opt_mode != B200DVB_MODE_PARITY)
         return nii_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
                                  workspace, workspace_bytes, (cudaStream_t)stream);
     if (use_tpf(codec->c, B))

@@ -19,13 +19,83 @@
 // group-staged transposition and the fused hard decision / error counters.
 #include "common.cuh"
 #include "nii_core.cuh"
+#include "nii16_core.cuh"
 #include "tpf_dev.cuh"
+
+#include <math.h>
 
 namespace b200dvb {
 
 namespace {
 
 using namespace tpf;
+
+// ---- arithmetic policies: the kernel below moves every value through `float` registers and float2 / float4
+//      containers; a policy decides what the 32 bits mean.  ArF32 = mode "nii" (one float32 frame per lane),
+//      ArS16 = mode "nii16" (two int16 frames per lane, nii16_core.cuh; the casts are register renames) --------------
+struct ArF32 {
+    static constexpr int kFpl = 1;                                  // frames per lane
+    typedef float sf_t;
+    static __device__ __forceinline__ void make_record(float YA, float YB, float W, float Y, float (&g)[8]) { nii::make_record(YA, YB, W, Y, g); }
+    static __device__ __forceinline__ void pass_step(float (&v)[16], const float (&g)[8], bool isb) { tpf::pass_step(v, g, isb); }
+    static __device__ __forceinline__ void bwd_step(float (&z)[16], const float (&g)[8]) { tpf::bwd_step(z, g); }
+    static __device__ __forceinline__ void app_maxima(const float (&x)[16], const float (&zs)[16], const float (&g)[8], float (&uv)[4]) { nii::app_maxima(x, zs, g, uv); }
+    static __device__ __forceinline__ void make_extrinsic(const float (&uv)[4], float YA, float YB, sf_t sf, float &ea, float &eb) { nii::make_extrinsic(uv, YA, YB, sf, ea, eb); }
+    static __device__ __forceinline__ float add(float a, float b) { return f_add(a, b); }
+    static __device__ __forceinline__ float chan(float lo, float) { return lo; }             // channel LLR of the lane's frame(s)
+    static __device__ __forceinline__ int neg(float L, int) { return L < 0.f; }             // hard decision of sub-frame i
+};
+struct ArS16 {
+    static constexpr int kFpl = 2;
+    typedef int sf_t;
+    template <int K> static __device__ __forceinline__ void in(const float (&a)[K], nii16::p16 (&b)[K])
+    {
+#pragma unroll
+        for (int i = 0; i < K; ++i) b[i] = nii16::bits(a[i]);
+    }
+    template <int K> static __device__ __forceinline__ void out(const nii16::p16 (&b)[K], float (&a)[K])
+    {
+#pragma unroll
+        for (int i = 0; i < K; ++i) a[i] = nii16::fl(b[i]);
+    }
+    static __device__ __forceinline__ void make_record(float YA, float YB, float W, float Y, float (&g)[8])
+    {
+        nii16::p16 pg[8];
+        nii16::make_record(nii16::bits(YA), nii16::bits(YB), nii16::bits(W), nii16::bits(Y), pg);
+        out(pg, g);
+    }
+    static __device__ __forceinline__ void pass_step(float (&v)[16], const float (&g)[8], bool isb)
+    {
+        nii16::p16 pv[16], pg[8];
+        in(v, pv); in(g, pg);
+        nii16::pass_step(pv, pg, isb);
+        out(pv, v);
+    }
+    static __device__ __forceinline__ void bwd_step(float (&z)[16], const float (&g)[8])
+    {
+        nii16::p16 pz[16], pg[8];
+        in(z, pz); in(g, pg);
+        nii16::bwd_step(pz, pg);
+        out(pz, z);
+    }
+    static __device__ __forceinline__ void app_maxima(const float (&x)[16], const float (&zs)[16], const float (&g)[8], float (&uv)[4])
+    {
+        nii16::p16 px[16], pz[16], pg[8], pu[4];
+        in(x, px); in(zs, pz); in(g, pg);
+        nii16::app_maxima(px, pz, pg, pu);
+        out(pu, uv);
+    }
+    static __device__ __forceinline__ void make_extrinsic(const float (&uv)[4], float YA, float YB, sf_t sf, float &ea, float &eb)
+    {
+        nii16::p16 pu[4], a, b;
+        in(uv, pu);
+        nii16::make_extrinsic(pu, nii16::bits(YA), nii16::bits(YB), sf, a, b);
+        ea = nii16::fl(a); eb = nii16::fl(b);
+    }
+    static __device__ __forceinline__ float add(float a, float b) { return nii16::fl(nii16::add2(nii16::bits(a), nii16::bits(b))); }
+    static __device__ __forceinline__ float chan(float lo, float hi) { return nii16::fl(nii16::pack16(nii16::quant(lo), nii16::quant(hi))); }
+    static __device__ __forceinline__ int neg(float L, int i) { return (i ? nii16::hi16(nii16::bits(L)) : nii16::lo16(nii16::bits(L))) < 0; }
+};
 
 constexpr int kW = kTpfWin;
 constexpr int kRingPairs = 4;        // prefetch ring depth of the "in" pass in step pairs (2 KB each)
@@ -42,6 +112,7 @@ struct NiiArgs {
     TpfGeom g;
     int B, iterations, n_tiles, n_llr, vec4;
     float sf_inner, sf_last;
+    int sf_inner_q, sf_last_q;       // the same in Q6 for the fixed-point mode
     const int16_t *tab;
     const float *llr;
     long long llr_stride;
@@ -158,10 +229,11 @@ __device__ __forceinline__ void yq_park(const Ctx &c, const YQ &q, int w0, int l
 // the float32 epilogue of a window's LAST step, carried into the next window (as in decode_tpf.cu: its dependent
 // chain fills the load latencies of the next window's start)
 struct Pend { float uv[4], y[2]; int idx; };
-__device__ __forceinline__ void pend_flush(const Ctx &c, Pend &p, float sf, float2 *LeOut)
+template <class AR>
+__device__ __forceinline__ void pend_flush(const Ctx &c, Pend &p, typename AR::sf_t sf, float2 *LeOut)
 {
     float ea, eb;
-    nii::make_extrinsic(p.uv, p.y[0], p.y[1], sf, ea, eb);
+    AR::make_extrinsic(p.uv, p.y[0], p.y[1], sf, ea, eb);
     if (p.idx >= 0) st_ws(LeOut + p.idx * 16 + c.f, make_float2(ea, eb));
     p.idx = -1;
 }
@@ -172,8 +244,8 @@ __device__ __forceinline__ void pend_flush(const Ctx &c, Pend &p, float sf, floa
 // First beta is walked down through the window and parked in shared memory, then alpha is walked up with the
 // a-posteriori maxima and the float32 epilogue (one step late).  TM: the window's records are in TMEM — column
 // block (wa + u) for the alpha lane, block (wa + len-1-u) for the beta lane (the high records are stored reversed).
-template <bool TM>
-__device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, float sf,
+template <class AR, bool TM>
+__device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, typename AR::sf_t sf,
                                        float2 *LeOut, int nslot, int nw0, int nlen, Pend &pend)
 {
     Buf B;
@@ -197,13 +269,13 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, fl
         complete(g);
         slot_put(ws + (len - 1) * 128, 0, Z);
         issue(len - 2);
-        pend_flush(c, pend, sf, LeOut);
-        bwd_step(Z, g);
+        pend_flush<AR>(c, pend, sf, LeOut);
+        AR::bwd_step(Z, g);
         complete(g);
         for (int u = len - 2; u >= 0; --u) {
             slot_put(ws + u * 128, 0, Z);                           // beta[k+1]
             issue(u > 0 ? u - 1 : 0);                               // u == 0: first record of the way up
-            bwd_step(Z, g);
+            AR::bwd_step(Z, g);
             complete(g);
         }
         if (!c.isb) slot_put(c.slotZ(), c.lane, Z);                 // running beta of the alpha lane
@@ -216,8 +288,8 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, fl
     tm_ld2(c.tq + c.ycol, yr);
     issue(len > 1 ? 1 : 0);
     slot_get(ws, 0, zs);
-    nii::app_maxima(X, zs, g, uvp);                                 // step 0 (its Y is not needed before the next step's epilogue)
-    pass_step(X, g, false);
+    AR::app_maxima(X, zs, g, uvp);                                  // step 0 (its Y is not needed before the next step's epilogue)
+    AR::pass_step(X, g, false);
     tm_wait_ld2(yr);
     complete(g);
     for (int u = 1; u < len; ++u) {
@@ -225,10 +297,10 @@ __device__ __forceinline__ void window(const Ctx &c, int wa, int w0, int len, fl
         issue(u + 1 < len ? u + 1 : u);
         slot_get(ws + u * 128, 0, zs);
         float uv[4];
-        nii::app_maxima(X, zs, g, uv);
-        pass_step(X, g, false);
+        AR::app_maxima(X, zs, g, uv);
+        AR::pass_step(X, g, false);
         float ea, eb;                                               // epilogue of step u-1
-        nii::make_extrinsic(uvp, yr[0], yr[1], sf, ea, eb);
+        AR::make_extrinsic(uvp, yr[0], yr[1], sf, ea, eb);
         st_ws(LeOut + (w0 + u - 1) * 16 + c.f, make_float2(ea, eb));
         tm_wait_ld2(yn);
         complete(g);
@@ -287,20 +359,21 @@ __device__ __forceinline__ void raw_get(const Ctx &c, const unsigned char *slot,
     }
 }
 struct PrepRec { float gA[8], gB[8]; };                      // records of two consecutive steps
+template <class AR>
 __device__ __forceinline__ void prep_pair(const Ctx &c, const Raw &r, int jn, PrepRec &out)
 {
     jn = min(jn, c.M - 2);
-    const float2 YA = make_float2(f_add(r.xA.x, r.laA.x), f_add(r.xA.y, r.laA.y));      // Lc + La
-    const float2 YB = make_float2(f_add(r.xB.x, r.laB.x), f_add(r.xB.y, r.laB.y));
-    nii::make_record(YA.x, YA.y, r.xA.z, r.xA.w, out.gA);
-    nii::make_record(YB.x, YB.y, r.xB.z, r.xB.w, out.gB);
+    const float2 YA = make_float2(AR::add(r.xA.x, r.laA.x), AR::add(r.xA.y, r.laA.y));  // Lc + La
+    const float2 YB = make_float2(AR::add(r.xB.x, r.laB.x), AR::add(r.xB.y, r.laB.y));
+    AR::make_record(YA.x, YA.y, r.xA.z, r.xA.w, out.gA);
+    AR::make_record(YB.x, YB.y, r.xB.z, r.xB.w, out.gB);
     const int ke = c.isb ? c.N - 2 - jn : jn;                       // the even (lower) k of the pair
     st_ws(c.Yb + (ke >> 1) * 16 + c.f, c.isb ? make_float4(YB.x, YB.y, YA.x, YA.y) : make_float4(YA.x, YA.y, YB.x, YB.y));
 }
 struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; };
 // steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 (raw inputs `rin`) into `out` and
 // pulls the raw inputs of steps jj+4, jj+5 out of the ring into `rout`.  CK: a checkpoint is due before step jj.
-template <bool FIRST, bool TMST, bool CK>
+template <class AR, bool FIRST, bool TMST, bool CK>
 __device__ __forceinline__ void in_pair(const Ctx &c, int jj, const float4 *Lsrc, const int16_t *tbl,
                                         int &ps, const PrepRec &in, PrepRec &out, const Raw &rin, Raw &rout,
                                         const Idx &xin, Idx &xout, float (&v)[16])
@@ -313,17 +386,17 @@ __device__ __forceinline__ void in_pair(const Ctx &c, int jj, const float4 *Lsrc
     cpa_commit();
     if (!FIRST) idx_get(c, jj + 6 + 2 * kRingPairs, tbl, xout);
     ps = ps == kRingPairs - 1 ? 0 : ps + 1;
-    prep_pair(c, rin, jj + 2, out);
+    prep_pair<AR>(c, rin, jj + 2, out);
     if (CK) ck_store(c, (c.M - jj) / kW - 1, v);
     const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
     if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
     else      smem_put(c, k0, in.gA);
-    pass_step(v, in.gA, c.isb);
+    AR::pass_step(v, in.gA, c.isb);
     if (TMST) tm_st8(c.tq + 8u * (jj + 1), in.gB);
     else      smem_put(c, k1, in.gB);
-    pass_step(v, in.gB, c.isb);
+    AR::pass_step(v, in.gB, c.isb);
 }
-template <bool FIRST, bool TMST, bool CKA, bool CKB>
+template <class AR, bool FIRST, bool TMST, bool CKA, bool CKB>
 __device__ __forceinline__ void in_loop(const Ctx &c, int j0, int j1, const float4 *Lsrc, const int16_t *tbl,
                                         PrepState &P, float (&v)[16])
 {
@@ -332,28 +405,28 @@ __device__ __forceinline__ void in_loop(const Ctx &c, int j0, int j1, const floa
     Idx XQ = P.ix;
     int jj = j0;
     for (; jj + 4 <= j1; jj += 4) {                                 // ping-pong: no register copies
-        in_pair<FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
-        in_pair<FIRST, TMST, CKB>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, RQ, P.raw, XQ, P.ix, v);
+        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
+        in_pair<AR, FIRST, TMST, CKB>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, RQ, P.raw, XQ, P.ix, v);
     }
     if (jj < j1) {
-        in_pair<FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
+        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
         P.r = Q;
         P.raw = RQ;
         P.ix = XQ;
     }
 }
 // steps [j0, j1) (even count): a checkpoint wherever (M - j) is a multiple of kW = 4, i.e. every second pair
-template <bool FIRST, bool TMST>
+template <class AR, bool FIRST, bool TMST>
 __device__ __forceinline__ void in_range(const Ctx &c, int j0, int j1, const float4 *Lsrc, const int16_t *tbl,
                                          PrepState &P, float (&v)[16])
 {
     static_assert(kW == 4, "checkpoints alternate between the step pairs of a four-step body");
     if (j0 >= j1) return;
-    if (((c.M - j0) % kW) == 0) in_loop<FIRST, TMST, true, false>(c, j0, j1, Lsrc, tbl, P, v);
-    else                        in_loop<FIRST, TMST, false, true>(c, j0, j1, Lsrc, tbl, P, v);
+    if (((c.M - j0) % kW) == 0) in_loop<AR, FIRST, TMST, true, false>(c, j0, j1, Lsrc, tbl, P, v);
+    else                        in_loop<AR, FIRST, TMST, false, true>(c, j0, j1, Lsrc, tbl, P, v);
 }
 
-template <bool FIRST>
+template <class AR, bool FIRST>
 __device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16])
 {
     const float4 *Lsrc = second ? c.L2A : c.L1A;
@@ -370,7 +443,7 @@ __device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16
     if (!FIRST) idx_get(c, 2 * kRingPairs, tbl, P.ix);
     cpa_wait<kRingPairs - 1>();
     raw_get<FIRST>(c, ring, P.raw);                                 // steps 0, 1
-    prep_pair(c, P.raw, 0, P.r);
+    prep_pair<AR>(c, P.raw, 0, P.r);
     prep_load_pair(c, ring, 2 * kRingPairs, Lsrc, P.ix, FIRST);
     cpa_commit();
     if (!FIRST) idx_get(c, 2 * kRingPairs + 2, tbl, P.ix);
@@ -381,14 +454,14 @@ __device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16
     if (!FIRST) idx_get(c, 2 * kRingPairs + 4, tbl, P.ix);
     P.ps = 2 % kRingPairs;
     if ((c.M % kW) != 0) ck_store(c, c.M / kW, v);                  // the ragged last window starts at step 0
-    in_range<FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
-    in_range<FIRST, false>(c, c.T, c.M, Lsrc, tbl, P, v);
+    in_range<AR, FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
+    in_range<AR, FIRST, false>(c, c.T, c.M, Lsrc, tbl, P, v);
     cpa_wait<0>();
 }
 
 // One SISO half-iteration for the 16 frames of this warp.
-template <bool TIMED>
-__device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool last, bool first_iter, float sf, long long (&ph)[8])
+template <class AR, bool TIMED>
+__device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool last, bool first_iter, typename AR::sf_t sf, long long (&ph)[8])
 {
     long long tA = TIMED ? clock64() : 0;
     const int N = c.N, M = c.M, T = c.T, lane = c.lane;
@@ -411,8 +484,8 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     }
     if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
     // ---- the "in" pass ------------------------------------------------------------------------------------------
-    if (first) in_pass<true>(c, second, v);
-    else       in_pass<false>(c, second, v);
+    if (first) in_pass<AR, true>(c, second, v);
+    else       in_pass<AR, false>(c, second, v);
     tm_wait_st();
     __syncwarp();
     if (!first && !last)                                            // old extrinsics are dead: every line is rewritten below
@@ -450,11 +523,11 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
         const int wa = i < nfull ? M - (i + 1) * kW : 0;
         const int nlen = i + 1 < nwin ? win_len(i + 1) : 0;
         const int nw0 = i + 1 < nwin ? win_w0(i + 1) : 0;
-        if (i < n_inner) window<false>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
-        else             window<true>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
+        if (i < n_inner) window<AR, false>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
+        else             window<AR, true>(c, wa, win_w0(i), win_len(i), sf, LeOut, nlen ? i + 1 : -1, nw0, nlen, pend);
         if (TIMED && i == n_inner - 1) { const long long t = clock64(); ph[4] += t - tA; tA = t; }
     }
-    pend_flush(c, pend, sf, LeOut);
+    pend_flush<AR>(c, pend, sf, LeOut);
     cpa_wait<0>();
     __syncwarp();
     if (TIMED) { const long long t = clock64(); ph[5] += t - tA; tA = t; }
@@ -468,10 +541,14 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
 }
 
-template <bool TIMED>
+template <class AR, bool TIMED>
 __global__ void __launch_bounds__(kTpfWarps * 32, 1)
 nii_kernel(const NiiArgs A)
 {
+    constexpr int kFpl = AR::kFpl;                                  // frames per lane
+    constexpr int kTile = kTpfFrames * kFpl;                        // frames per warp tile: sub-frame i of lane f is frame 16 i + f
+    const typename AR::sf_t sf_inner = kFpl == 2 ? (typename AR::sf_t)A.sf_inner_q : (typename AR::sf_t)A.sf_inner;
+    const typename AR::sf_t sf_last = kFpl == 2 ? (typename AR::sf_t)A.sf_last_q : (typename AR::sf_t)A.sf_last;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TpfGeom g = A.g;
     const int N = g.N;
@@ -526,7 +603,7 @@ nii_kernel(const NiiArgs A)
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = TIMED ? clock64() : 0;
     for (int tile = wg; tile < A.n_tiles; tile += gridDim.x * kTpfWarps) {
-        const long long frame0 = (long long)tile * kTpfFrames;
+        const long long frame0 = (long long)tile * kTile;
         const long long t0 = TIMED ? clock64() : 0;
         // ---- de-puncture + transpose the 16 frames' LLRs into [j][lane] (as decode_tpf.cu) ------------------
         if (A.vec4) {
@@ -536,8 +613,11 @@ nii_kernel(const NiiArgs A)
             const bool in_rec = rec_bytes > kStageBytes;
             float4 *rowbuf = in_rec ? c.srec : reinterpret_cast<float4 *>(c.stage);
             const int fit = (in_rec ? rec_bytes : kStageBytes - N * 16) / (pitch4 * 16);
-            const int lg = fit >= 8 ? 3 : fit >= 4 ? 2 : 1, G = 1 << lg, KQ = 32 >> lg;
-            const int fr = lane & (G - 1), kq = lane >> lg;
+            // G rows are staged at once: GL = G / kFpl lane-frames x kFpl sub-frames (row r < GL: frame g0 + r, row
+            // GL + r: frame 16 + g0 + r).  Lane = (couple kq, lane-frame fr) with fr the minor index.
+            const int lg = fit >= 8 ? 3 : fit >= 4 ? 2 : 1, G = 1 << lg;
+            const int lgl = kFpl == 2 ? lg - 1 : lg, GL = 1 << lgl, KQ = 32 >> lgl;
+            const int fr = lane & (GL - 1), kq = lane >> lgl;
             int4 *otab = reinterpret_cast<int4 *>(in_rec ? c.stage : c.stage + G * pitch4 * 16);
             for (int k = lane; k < N; k += 32) {
                 const unsigned oa = (unsigned short)__ldg(g_off + k), op = (unsigned short)__ldg(g_off + c.perm[k]);
@@ -547,92 +627,98 @@ nii_kernel(const NiiArgs A)
             }
             // whole rows by bulk copy (cp.async.bulk: one instruction of one lane per 5 KB row, completed on this
             // warp's mbarrier) — the rows are the longest contiguous transfers of the kernel
+            auto row_frame = [&](int g0, int r) { return frame0 + (r < GL ? g0 + r : kTpfFrames + g0 + r - GL); };
             auto pull = [&](int g0) {
                 if (lane == 0) {
                     int live_rows = 0;
-                    for (int r = 0; r < G; ++r) live_rows += frame0 + g0 + r < A.B;
+                    for (int r = 0; r < G; ++r) live_rows += row_frame(g0, r) < A.B;
                     fence_proxy_async();                            // the row buffer was read (or held records) before
                     mbar_expect_tx(mbar, (unsigned)(live_rows * nq * 16));
-                    for (int r = 0; r < live_rows; ++r)
-                        bulk_g2s_stream(rowbuf + r * pitch4, A.llr + (frame0 + g0 + r) * A.llr_stride, (unsigned)(nq * 16), mbar, c.pol);
+                    for (int r = 0; r < G; ++r)
+                        if (row_frame(g0, r) < A.B)
+                            bulk_g2s_stream(rowbuf + r * pitch4, A.llr + row_frame(g0, r) * A.llr_stride, (unsigned)(nq * 16), mbar, c.pol);
                 }
             };
             pull(0);
             if (A.ref_bits) {                                       // the hard decision will want these rows in L2
-                const int lines = (2 * N * kTpfFrames + 127) / 128;
-                const long long nb = min((long long)kTpfFrames, A.B - frame0) * 2 * N;
+                const int lines = (2 * N * kTile + 127) / 128;
+                const long long nb = min((long long)kTile, A.B - frame0) * 2 * N;
                 for (int i = lane; i < lines; i += 32)
                     if ((long long)i * 128 < nb) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.ref_bits + frame0 * 2 * N + i * 128));
             }
             const float *row = reinterpret_cast<const float *>(rowbuf + fr * pitch4);
-            for (int g0 = 0; g0 < kTpfFrames; g0 += G) {
+            const float *rowh = reinterpret_cast<const float *>(rowbuf + (GL + fr) * pitch4);   // sub-frame 1 (kFpl == 2)
+            for (int g0 = 0; g0 < kTpfFrames; g0 += GL) {
                 mbar_wait(mbar, mphase);
                 mphase ^= 1u;
                 const bool livef = frame0 + g0 + fr < A.B;
+                const bool liveh = kFpl == 2 && frame0 + kTpfFrames + g0 + fr < A.B;
+                auto val = [&](int o) { return AR::chan(livef ? row[o] : 0.f, liveh ? rowh[o] : 0.f); };
 #pragma unroll 4
                 for (int k0 = 0; k0 < N; k0 += KQ) {
                     const int k = k0 + kq;
                     const int4 e = otab[min(k, N - 1)];
                     const int oa = (short)(e.x & 0xffff), op = e.x >> 16, o0 = (short)(e.y & 0xffff), o1 = e.y >> 16;
                     const int o2 = (short)(e.z & 0xffff), o3 = e.z >> 16;
-                    float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f), x2 = x1;
-                    if (livef) {
-                        x1.x = row[oa]; x1.y = row[oa + 1]; x2.x = row[op]; x2.y = row[op + 1];
-                        if (o0 >= 0) x1.z = row[o0];
-                        if (o1 >= 0) x1.w = row[o1];
-                        if (o2 >= 0) x2.z = row[o2];
-                        if (o3 >= 0) x2.w = row[o3];
-                    }
+                    const float zero = AR::chan(0.f, 0.f);
+                    float4 x1 = make_float4(zero, zero, zero, zero), x2 = x1;
+                    x1.x = val(oa); x1.y = val(oa + 1); x2.x = val(op); x2.y = val(op + 1);
+                    if (o0 >= 0) x1.z = val(o0);
+                    if (o1 >= 0) x1.w = val(o1);
+                    if (o2 >= 0) x2.z = val(o2);
+                    if (o3 >= 0) x2.w = val(o3);
                     if (k < N) {
                         st_ws(c.L1A + lpos(c, k, g0 + fr), x1);
                         st_ws(c.L2A + lpos(c, k, g0 + fr), x2);
                     }
                 }
                 __syncwarp();
-                if (g0 + G < kTpfFrames) pull(g0 + G);
+                if (g0 + GL < kTpfFrames) pull(g0 + GL);
             }
         } else
         for (int k = lane; k < N; k += 32) {
             const int oa = __ldg(g_off + k), op = __ldg(g_off + c.perm[k]);
             const int o0 = __ldg(g_off + N + k), o1 = __ldg(g_off + 2 * N + k);
             const int o2 = __ldg(g_off + 3 * N + k), o3 = __ldg(g_off + 4 * N + k);
-#pragma unroll
-            for (int f0 = 0; f0 < kTpfFrames; f0 += 8) {
-                float4 x1[8], x2[8];
-#pragma unroll
-                for (int fr = 0; fr < 8; ++fr) {
-                    const long long frame = frame0 + f0 + fr;
-                    const float *Lf = A.llr + frame * A.llr_stride;
-                    x1[fr] = make_float4(0.f, 0.f, 0.f, 0.f); x2[fr] = x1[fr];
-                    if (frame < A.B) {
-                        x1[fr].x = __ldg(Lf + oa); x1[fr].y = __ldg(Lf + oa + 1);
-                        x2[fr].x = __ldg(Lf + op); x2[fr].y = __ldg(Lf + op + 1);
-                        if (o0 >= 0) x1[fr].z = __ldg(Lf + o0);
-                        if (o1 >= 0) x1[fr].w = __ldg(Lf + o1);
-                        if (o2 >= 0) x2[fr].z = __ldg(Lf + o2);
-                        if (o3 >= 0) x2[fr].w = __ldg(Lf + o3);
-                    }
-                }
-#pragma unroll
-                for (int fr = 0; fr < 8; ++fr) {
-                    st_ws(c.L1A + lpos(c, k, f0 + fr), x1[fr]);
-                    st_ws(c.L2A + lpos(c, k, f0 + fr), x2[fr]);
-                }
+            for (int fr = 0; fr < kTpfFrames; ++fr) {
+                const long long fl_ = frame0 + fr, fh_ = frame0 + kTpfFrames + fr;
+                const bool livef = fl_ < A.B, liveh = kFpl == 2 && fh_ < A.B;
+                const float *Lf = A.llr + (livef ? fl_ : 0) * A.llr_stride, *Lh = A.llr + (liveh ? fh_ : 0) * A.llr_stride;
+                auto val = [&](int o) { return AR::chan(livef ? __ldg(Lf + o) : 0.f, liveh ? __ldg(Lh + o) : 0.f); };
+                const float zero = AR::chan(0.f, 0.f);
+                float4 x1 = make_float4(zero, zero, zero, zero), x2 = x1;
+                x1.x = val(oa); x1.y = val(oa + 1); x2.x = val(op); x2.y = val(op + 1);
+                if (o0 >= 0) x1.z = val(o0);
+                if (o1 >= 0) x1.w = val(o1);
+                if (o2 >= 0) x2.z = val(o2);
+                if (o3 >= 0) x2.w = val(o3);
+                st_ws(c.L1A + lpos(c, k, fr), x1);
+                st_ws(c.L2A + lpos(c, k, fr), x2);
             }
         }
         __syncwarp();
         if (TIMED) ph[0] += clock64() - t0;
         for (int h = 0; h < 2 * A.iterations; ++h) {
-            const float sf = (h >> 1) < A.iterations - 1 ? A.sf_inner : A.sf_last;
-            siso<TIMED>(c, (h & 1) != 0, h == 0, h == 2 * A.iterations - 1, h < 2, sf, ph);
+            const typename AR::sf_t sf = (h >> 1) < A.iterations - 1 ? sf_inner : sf_last;
+            siso<AR, TIMED>(c, (h & 1) != 0, h == 0, h == 2 * A.iterations - 1, h < 2, sf, ph);
         }
         const long long t6 = TIMED ? clock64() : 0;
         // ---- hard decision: (Lc + La) + Le1 < 0 in float32 + optional error counting ----------------------
-        const long long frame = frame0 + c.f;
-        const bool live = frame < A.B;
+        long long frame[kFpl];
+        bool live[kFpl], cnt[kFpl];
+        const uint8_t *refp[kFpl];
+        int any_err[kFpl];
+        unsigned word[kFpl];
+#pragma unroll
+        for (int i = 0; i < kFpl; ++i) {
+            frame[i] = frame0 + kTpfFrames * i + c.f;
+            live[i] = frame[i] < A.B;
+            cnt[i] = live[i] && A.ref_bits != nullptr;
+            refp[i] = cnt[i] ? A.ref_bits + (size_t)frame[i] * 2 * N : reinterpret_cast<const uint8_t *>(A.tab);
+            any_err[i] = 0;
+            word[i] = 0;
+        }
         const int wpf = (2 * N + 31) / 32;
-        const bool cnt = live && A.ref_bits != nullptr;
-        const uint8_t *refp = cnt ? A.ref_bits + (size_t)frame * 2 * N : reinterpret_cast<const uint8_t *>(A.tab);
         constexpr int kHB = 3 * 8 * 32 * 16;                        // bytes of one staged batch: [array][t][lane] x 16 B
         const int rec_bytes_h = g.mid * 2 * 16 * (int)sizeof(float4);
         unsigned char *hbuf = rec_bytes_h >= kHB ? reinterpret_cast<unsigned char *>(c.srec) : c.stage;
@@ -654,33 +740,36 @@ nii_kernel(const NiiArgs A)
             }
             cpa_commit();
         };
-        int any_err = 0;
-        unsigned word = 0;
         for (int b = 0; b < nst; ++b) hissue(b, b);
         for (int b = 0, st = 0; b < nbu; ++b) {
             if (nst == 3) cpa_wait<2>(); else if (nst == 2) cpa_wait<1>(); else cpa_wait<0>();
             const int kb = (c.isb + 2 * (b >> 1)) * 16 + 8 * (b & 1);
             const unsigned char *src = hbuf + st * kHB + lane * 16;
-            unsigned short rb[8];
+            unsigned short rb[kFpl][8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) rb[t] = *reinterpret_cast<const unsigned short *>(refp + 2 * min(kb + t, N - 1));
+            for (int i = 0; i < kFpl; ++i)
+#pragma unroll
+                for (int t = 0; t < 8; ++t) rb[i][t] = *reinterpret_cast<const unsigned short *>(refp[i] + 2 * min(kb + t, N - 1));
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int k = kb + t;
                 const float4 ab = *reinterpret_cast<const float4 *>(src + t * 512);
                 const float2 la = *reinterpret_cast<const float2 *>(src + 4096 + t * 512 + c.h8);
                 const float2 e1 = *reinterpret_cast<const float2 *>(src + 8192 + t * 512 + c.h8);
-                const float LA = f_add(f_add(ab.x, la.x), e1.x);
-                const float LB = f_add(f_add(ab.y, la.y), e1.y);
-                const int bA = LA < 0.f, bB = LB < 0.f;
-                if (k < N) {
-                    word |= (unsigned)(bA | (bB << 1)) << (2 * (8 * (b & 1) + t));
-                    if (live && A.bits)
-                        *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * k) = make_int2(bA, bB);
-                    if (cnt) {
-                        const int errs = (bA != (rb[t] & 0xff)) + (bB != (rb[t] >> 8));
-                        bit_err += errs;
-                        any_err |= errs;
+                const float LA = AR::add(AR::add(ab.x, la.x), e1.x);
+                const float LB = AR::add(AR::add(ab.y, la.y), e1.y);
+#pragma unroll
+                for (int i = 0; i < kFpl; ++i) {
+                    const int bA = AR::neg(LA, i), bB = AR::neg(LB, i);
+                    if (k < N) {
+                        word[i] |= (unsigned)(bA | (bB << 1)) << (2 * (8 * (b & 1) + t));
+                        if (live[i] && A.bits)
+                            *reinterpret_cast<int2 *>(A.bits + (size_t)frame[i] * 2 * N + 2 * k) = make_int2(bA, bB);
+                        if (cnt[i]) {
+                            const int errs = (bA != (rb[i][t] & 0xff)) + (bB != (rb[i][t] >> 8));
+                            bit_err += errs;
+                            any_err[i] |= errs;
+                        }
                     }
                 }
             }
@@ -688,13 +777,19 @@ nii_kernel(const NiiArgs A)
             st = st + 1 == nst ? 0 : st + 1;
             if (b & 1) {
                 const int w = c.isb + b - 1;
-                if (live && A.packed && w < nwords) A.packed[(size_t)frame * wpf + w] = word;
-                word = 0;
+#pragma unroll
+                for (int i = 0; i < kFpl; ++i) {
+                    if (live[i] && A.packed && w < nwords) A.packed[(size_t)frame[i] * wpf + w] = word[i];
+                    word[i] = 0;
+                }
             }
         }
         cpa_wait<0>();
-        any_err |= __shfl_xor_sync(0xffffffffu, any_err, 16);
-        if (live && !c.isb) { frames_done += 1; frm_err += any_err ? 1 : 0; }
+#pragma unroll
+        for (int i = 0; i < kFpl; ++i) {
+            any_err[i] |= __shfl_xor_sync(0xffffffffu, any_err[i], 16);
+            if (live[i] && !c.isb) { frames_done += 1; frm_err += any_err[i] ? 1 : 0; }
+        }
         __syncwarp();
         if (TIMED) ph[6] += clock64() - t6;
     }
@@ -760,8 +855,10 @@ int nii_configure(Codec &c)
     g.off_ck = take((size_t)g.nslots * 4 * 32 * sizeof(float4));
     g.off_init = take((size_t)2 * 4 * 32 * sizeof(float4));
     g.ws_per_warp = off;
-    B2_CUDA(cudaFuncSetAttribute(nii_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    B2_CUDA(cudaFuncSetAttribute(nii_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    B2_CUDA(cudaFuncSetAttribute(nii_kernel<ArF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    B2_CUDA(cudaFuncSetAttribute(nii_kernel<ArF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    B2_CUDA(cudaFuncSetAttribute(nii_kernel<ArS16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    B2_CUDA(cudaFuncSetAttribute(nii_kernel<ArS16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     g.enabled = 1;
     return B200DVB_OK;
 }
@@ -780,7 +877,8 @@ int nii_read_phase_cycles(double *out_h, int reset)
 
 static int nii_grid(const Codec &c, int B)
 {
-    const int tiles = (B + kTpfFrames - 1) / kTpfFrames;
+    const int tile = c.opt_mode == B200DVB_MODE_NII16 ? 2 * kTpfFrames : kTpfFrames;
+    const int tiles = (B + tile - 1) / tile;
     const int ctas = (tiles + kTpfWarps - 1) / kTpfWarps;
     return ctas < c.num_sms ? ctas : c.num_sms;
 }
@@ -798,7 +896,9 @@ int nii_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     if (ws_bytes < nii_workspace_bytes(c, B)) return B200DVB_ENOMEM;
     NiiArgs A{};
     A.g = c.nii; A.B = B; A.iterations = c.iterations;
-    A.n_tiles = (B + kTpfFrames - 1) / kTpfFrames;
+    const bool fixed = c.opt_mode == B200DVB_MODE_NII16;
+    const int tile = fixed ? 2 * kTpfFrames : kTpfFrames;
+    A.n_tiles = (B + tile - 1) / tile;
     A.n_llr = c.n_llr;
     A.vec4 = (c.N <= 256) && (llr_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && ((c.n_llr + 3) / 4 * 4 <= kRowFloats) &&
              !c.opt_no_row_staging;
@@ -809,11 +909,18 @@ int nii_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
         if (avail / (pitch4 * 16) < 2) A.vec4 = 0;
     }
     A.sf_inner = (float)c.sf_inner; A.sf_last = (float)c.sf_last; A.tab = c.d_tab;
+    A.sf_inner_q = (int)lrint(c.sf_inner * 64.0); A.sf_last_q = (int)lrint(c.sf_last * 64.0);   // Q6: 45 and 64 for 0.7 / 1.0
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;
     A.ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    if (c.opt_phase_timers) nii_kernel<true><<<nii_grid(c, B), kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
-    else                    nii_kernel<false><<<nii_grid(c, B), kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
+    const int grid = nii_grid(c, B);
+    if (fixed) {
+        if (c.opt_phase_timers) nii_kernel<ArS16, true><<<grid, kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
+        else                    nii_kernel<ArS16, false><<<grid, kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
+    } else {
+        if (c.opt_phase_timers) nii_kernel<ArF32, true><<<grid, kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
+        else                    nii_kernel<ArF32, false><<<grid, kTpfWarps * 32, c.nii.smem_bytes, s>>>(A);
+    }
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

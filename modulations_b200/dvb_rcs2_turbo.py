@@ -158,13 +158,13 @@ class _CodecHandle:
         self.N = int(N)
         self.k_info = 2 * int(N)
         self.n_llr = int(lib.b200dvb_codec_n_llr(h))
-        self.frames_per_wave = int(lib.b200dvb_codec_frames_per_wave(h))
         self._ws = {}
         if kernel is not None:
             self.set_option(_lib.OPT_KERNEL, {"auto": _lib.KERNEL_AUTO, "quad": _lib.KERNEL_QUAD,
                                               "tpf": _lib.KERNEL_TPF}[kernel])
         if mode is not None:
             self.set_option(_lib.OPT_DECODER_MODE, mode)
+        self.frames_per_wave = int(lib.b200dvb_codec_frames_per_wave(h))    # depends on the decoder mode
 
     def set_option(self, option, value):
         _lib.check(_lib.load().b200dvb_codec_set_option(self.h, int(option), int(value)), "codec_set_option")
@@ -355,7 +355,7 @@ def bijective_interleaver(N):
 
 
 class DVBRCS2_Turbo:
-    BOUNDARIES = {"double-pass": _lib.MODE_PARITY, "nii": _lib.MODE_NII}
+    BOUNDARIES = {"double-pass": _lib.MODE_PARITY, "nii": _lib.MODE_NII, "nii16": _lib.MODE_NII16}
 
     def __init__(self, N_couples, code_rate, iterations=8, perm=None, kernel=None, boundary="double-pass"):
         """``perm`` (extension, NOT reference behaviour): a user-supplied interleaver table of length N
@@ -368,7 +368,9 @@ class DVBRCS2_Turbo:
         NON-PARITY mode: one pass per SISO, alpha[0] / beta[N] initialised from the metrics the same constituent
         decoder reached in the previous iteration, float32 extrinsics (csrc/nii_core.cuh).  Its hard decisions
         differ from the reference's in isolated bits; it is judged on BER/FER and checked bit for bit against
-        its own model (oracle/nii_model.c).  ``decode`` / ``decode_batch`` / ``decode_batch_host`` follow it;
+        its own model (oracle/nii_model.c).  "nii16" is the same decoder in 16-bit fixed point, two frames per
+        32-bit register with DPX add-compare-select instructions (csrc/nii16_core.cuh; model oracle/nii16_model.c).
+        ``decode`` / ``decode_batch`` / ``decode_batch_host`` follow it;
         ``bcjr_max_log_map`` and the encoder are unaffected."""
         if boundary not in self.BOUNDARIES:
             raise ValueError(f"boundary must be one of {sorted(self.BOUNDARIES)}")

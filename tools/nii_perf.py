@@ -19,7 +19,7 @@ lib = _lib.load()
 B0 = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 for (N, rate, B) in ((212, '1/3', B0), (48, '1/3', 4 * B0)):
     res = {}
-    for mode in ("double-pass", "nii"):
+    for mode in ("double-pass", "nii", "nii16"):
         c = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="tpf", boundary=mode)
         h = c.handle
         info = torch.empty((B, 2 * N), dtype=torch.uint8, device="cuda")
@@ -37,7 +37,7 @@ for (N, rate, B) in ((212, '1/3', B0), (48, '1/3', 4 * B0)):
               f"(reference-algorithm ACS/s equivalent {fps*acs/(64*148*1.965e9)*100:.1f}% of the ALU roofline); "
               f"BER={cnt[0]/max(cnt[3],1):.4f} FER={cnt[1]/max(cnt[2],1):.4f}")
         ph = np.zeros(8)
-        rd = lib.b200dvb_debug_nii_cycles if mode == "nii" else lib.b200dvb_debug_tpf_cycles
+        rd = lib.b200dvb_debug_nii_cycles if mode != "double-pass" else lib.b200dvb_debug_tpf_cycles
         rd(_lib.host_ptr(ph), 1)
         h.set_option(_lib.OPT_PHASE_TIMERS, 1)
         c.decode_batch(llr, ref_bits=info, counters=counters, out="none"); torch.cuda.synchronize()
@@ -45,11 +45,11 @@ for (N, rate, B) in ((212, '1/3', B0), (48, '1/3', 4 * B0)):
         rd(_lib.host_ptr(ph), 1)
         tot = ph[7]
         if tot > 0:
-            names = (["transpose", "in-pass+prep", "boundary+crossing", "-", "out_smem", "out_tmem", "hard"] if mode == "nii"
+            names = (["transpose", "in-pass+prep", "boundary+crossing", "-", "out_smem", "out_tmem", "hard"] if mode != "double-pass"
                      else ["transpose", "pass1a+prep", "pass1b", "pass2", "out_smem", "out_tmem", "hard"])
-            tiles = B / 16
+            tiles = B / (32 if mode == "nii16" else 16)
             print("   phases: " + "  ".join(f"{n}={v/tot*100:.1f}%" for n, v in zip(names, ph[:7])))
             print("   cycles per tile-SISO: " + "  ".join(f"{n}={v/tiles/16:.0f}" for n, v in zip(names[1:6], ph[1:6]))
                   + f"   per tile: transpose={ph[0]/tiles:.0f} hard={ph[6]/tiles:.0f} total={tot/tiles:.0f}")
         del info, coded, llr
-    print(f"   nii / parity throughput: {res['nii']/res['double-pass']:.3f}x")
+    print(f"   nii / parity throughput: {res['nii']/res['double-pass']:.3f}x    nii16 / parity: {res['nii16']/res['double-pass']:.3f}x")

@@ -93,7 +93,10 @@ def test_nii_ber_inside_parity_confidence_interval(mode):
     committed table floors FER at 1): each mode's counts must lie inside the 99 % binomial interval
     (normal approximation, 2.576 sigma of the pooled estimate) of the other's.  (The frames are the same, so the
     two estimates are positively correlated and the test is conservative in the right direction: a real difference
-    larger than the interval of INDEPENDENT samples fails.)"""
+    larger than the interval of INDEPENDENT samples fails.)  The fixed-point mode additionally gets a stated
+    quantisation allowance of 1 % RELATIVE (LLRs in 1/4 units, 9-bit extrinsics): with 55 M bits per point the
+    binomial interval is 0.17 % of the BER at 2 dB and resolves the format's real cost (measured: +0.29 % of the BER at
+    2 dB, i.e. a few thousandths of a dB; profiles/r02_ber_three_modes.txt)."""
     import torch
     from modulations_b200 import dvb_rcs2_turbo as turbo
     N, rate, B = 212, '1/3', 1 << 17
@@ -115,6 +118,8 @@ def test_nii_ber_inside_parity_confidence_interval(mode):
         for what, e0, e1, n in (("BER", c0[0], c1[0], c0[3]), ("FER", c0[1], c1[1], c0[2])):
             p = (e0 + e1) / (2 * n)
             half = 2.576 * np.sqrt(max(p * (1 - p), 1e-12) * 2 / n)
+            if mode == "nii16":
+                half = max(half, 0.01 * e0 / n)
             assert abs(e0 / n - e1 / n) <= half + 1e-12, (ebn0, what, e0 / n, e1 / n, half)
 
 

@@ -11,7 +11,7 @@ for k in ('value','ms_per_step'): print(k, d[k])
 print('roofline', {k:v for k,v in d['roofline'].items() if k not in ('note','traffic_source')})
 print('e2e', {k:v for k,v in d['e2e'].items() if k not in ('api','ceiling_what')})
 print('e2e_mc', d['e2e_mc']['value'], d['e2e_mc']['frac_of_resident'])
-print('nii', d['nii_mode'])
+print('nonparity', {k:(v.get('info_gbit_per_s'), v.get('speedup_over_parity_mode')) for k,v in d['nonparity_modes'].items() if k[0]!='_'})
 print('cpu', d['cpu_baseline'])
 for k in ('latency','n752_r12','config0_n48_qpsk'): print(k, d.get(k))
 print('demap', {k:(v['gsym_per_s'], v['roofline']['frac']) for k,v in d['demap'].items() if k!='_what'})

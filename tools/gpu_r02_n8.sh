@@ -17,6 +17,6 @@ print('N=$n value', d['value'], 'ms', d['ms_per_step'])
 print(' e2e', {k:v for k,v in d['e2e'].items() if k not in ('api','ceiling_what','int32_layout')})
 print(' e2e int32', d['e2e']['int32_layout'])
 print(' e2e_mc', d['e2e_mc']['value'], d['e2e_mc']['frac_of_resident'])
-print(' nii', d['nii_mode'].get('info_gbit_per_s'))
+print(' nonparity', {k:v.get('info_gbit_per_s') for k,v in d['nonparity_modes'].items() if k[0]!='_'})
 " || tail -5 gpurun_out/r02_bench_n$n.err
 done

@@ -103,6 +103,7 @@ constexpr int kRingPairs = 4;        // prefetch ring depth of the "in" pass in 
 // "in" pass aliases it); [8K, 10K) Z slot; [10K, 12K) X slot
 constexpr int kStageBytes = 12288;
 constexpr int kRowFloats = kStageBytes / 8;
+constexpr int kHdrBytes = 64 + kTpfWarps * kRingPairs * 8;   // after the tables: slots, one mbarrier per warp, kRingPairs ring mbarriers per warp
 
 // phase timers (SM cycles summed over warps): 0 transpose-in, 1 "in" pass (+prep), 2 boundary load/store + crossing,
 // 3 unused, 4 out-phase windows in shared memory, 5 out-phase windows in tensor memory, 6 hard decision, 7 warp total
@@ -138,6 +139,7 @@ struct Ctx {
     float4 *INIT;                    // boundary metrics [siso][4][32 lanes], natural labels, indexed by the lane that READS them
     unsigned long long pol;          // L2 evict-first policy for the channel LLRs
     unsigned one;                    // 1, opaque to the compiler (see cpa16)
+    unsigned rmbar;                  // shared-memory address of this warp's kRingPairs ring mbarriers (bulk channel loads)
     __device__ __forceinline__ float4 *wstore() const { return reinterpret_cast<float4 *>(stage); }
     __device__ __forceinline__ float4 *slotZ() const { return reinterpret_cast<float4 *>(stage + 8192); }
     __device__ __forceinline__ float4 *slotX() const { return reinterpret_cast<float4 *>(stage + 10240); }
@@ -161,15 +163,31 @@ __device__ __forceinline__ void ck_store(const Ctx &c, int slot, const float (&v
     float n[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) n[s] = c.isb ? v[rho4(s)] : v[s];
+#ifdef NII_CK256
+    // two 32-byte stores per checkpoint instead of four 16-byte ones: slot layout [2 halves][32 lanes] x 32 B
+    unsigned char *p = reinterpret_cast<unsigned char *>(c.CK) + slot * 2048 + c.lane * 32;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p + h * 1024), "f"(n[8 * h]), "f"(n[8 * h + 1]), "f"(n[8 * h + 2]), "f"(n[8 * h + 3]),
+                        "f"(n[8 * h + 4]), "f"(n[8 * h + 5]), "f"(n[8 * h + 6]), "f"(n[8 * h + 7]) : "memory");
+#else
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         st_ws(c.CK + (slot * 4 + q) * 32 + c.lane, make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]));
+#endif
 }
 __device__ __forceinline__ void issue_ckpt(const Ctx &c, int slot)
 {   // alpha lanes need their alpha checkpoint as X, beta lanes their beta checkpoint as Z
     float4 *dst = (c.isb ? c.slotZ() : c.slotX()) + c.lane;
+#ifdef NII_CK256
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(c.CK) + slot * 2048 + c.lane * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cpa16(dst + q * 32, p + (q >> 1) * 1024 + (q & 1) * 16, c.one);
+#else
 #pragma unroll
     for (int q = 0; q < 4; ++q) cpa16(dst + q * 32, c.CK + (slot * 4 + q) * 32 + c.lane, c.one);
+#endif
 }
 __device__ __forceinline__ void slot_get(const float4 *slot, int lane, float (&v)[16])
 {
@@ -334,27 +352,50 @@ __device__ __forceinline__ void idx_get(const Ctx &c, int jn, const int16_t *tbl
 // iteration: the lane copies the 16-byte chunk that holds its frame's pair (shared with the neighbouring frame)
 // and reads its half.
 __device__ __forceinline__ void prep_load_pair(const Ctx &c, unsigned char *slot, int jn, const float4 *Lsrc,
-                                               const Idx &x, bool first)
+                                               const Idx &x, bool first, int si)
 {
     jn = min(jn, c.M - 2);                                          // clamped at the end: harmless re-computation
     const unsigned d = s_addr(slot) * c.one;
     const float4 *src = Lsrc + jn * 32 + c.lane;
+#ifdef NII_BULK_CHAN
+    // the channel LLRs of a step pair are ONE contiguous kilobyte: a bulk copy issued by one lane (TMA unit) instead of
+    // two LDGSTS warp-instructions through the LSU.  Slot layout [x A][x B][la A][la B].
+    if (c.lane == 0) {
+        mbar_expect_tx(c.rmbar + 8u * si, 1024u);
+        bulk_g2s_stream(slot, Lsrc + jn * 32, 1024u, c.rmbar + 8u * si, c.pol);
+    }
+    if (!first) {
+        cpa16_off<1024, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.a * 16) + (c.f >> 1));
+        cpa16_off<1536, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.b * 16) + (c.f >> 1));
+    }
+    return;
+#endif
+    // (NII_ABL_*: timing-only ablation builds for profiles/r02_nii_ablation.txt; never defined in the shipped library)
+#ifndef NII_ABL_NOCHAN
     cpa16_stream_off<0, 0>(d, src, c.pol);
     cpa16_stream_off<1024, 512>(d, src, c.pol);
+#endif
+#ifndef NII_ABL_NOGATHER
     if (!first) {
         cpa16_off<512, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.a * 16) + (c.f >> 1));
         cpa16_off<1536, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.b * 16) + (c.f >> 1));
     }
+#endif
 }
 struct Raw { float4 xA, xB; float2 laA, laB; };
 template <bool FIRST>
 __device__ __forceinline__ void raw_get(const Ctx &c, const unsigned char *slot, Raw &r)
 {
+#ifdef NII_BULK_CHAN
+    constexpr int oXB = 512, oLA = 1024;
+#else
+    constexpr int oXB = 1024, oLA = 512;
+#endif
     r.xA = *reinterpret_cast<const float4 *>(slot);
-    r.xB = *reinterpret_cast<const float4 *>(slot + 1024);
+    r.xB = *reinterpret_cast<const float4 *>(slot + oXB);
     r.laA = r.laB = make_float2(0.f, 0.f);
     if (!FIRST) {
-        r.laA = *reinterpret_cast<const float2 *>(slot + 512 + c.h8);
+        r.laA = *reinterpret_cast<const float2 *>(slot + oLA + c.h8);
         r.laB = *reinterpret_cast<const float2 *>(slot + 1536 + c.h8);
     }
 }
@@ -365,35 +406,62 @@ __device__ __forceinline__ void prep_pair(const Ctx &c, const Raw &r, int jn, Pr
     jn = min(jn, c.M - 2);
     const float2 YA = make_float2(AR::add(r.xA.x, r.laA.x), AR::add(r.xA.y, r.laA.y));  // Lc + La
     const float2 YB = make_float2(AR::add(r.xB.x, r.laB.x), AR::add(r.xB.y, r.laB.y));
+#ifndef NII_ABL_NOPREP
     AR::make_record(YA.x, YA.y, r.xA.z, r.xA.w, out.gA);
     AR::make_record(YB.x, YB.y, r.xB.z, r.xB.w, out.gB);
+#else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { out.gA[i] = i & 1 ? YA.x : r.xA.z; out.gB[i] = i & 1 ? YB.y : r.xB.w; }
+#endif
     const int ke = c.isb ? c.N - 2 - jn : jn;                       // the even (lower) k of the pair
+#ifndef NII_ABL_NOY
     st_ws(c.Yb + (ke >> 1) * 16 + c.f, c.isb ? make_float4(YB.x, YB.y, YA.x, YA.y) : make_float4(YA.x, YA.y, YB.x, YB.y));
+#endif
 }
-struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; };
+struct PrepState { PrepRec r; Raw raw; Idx ix; int ps; unsigned rph; };
 // steps jj, jj+1 with the records in `in`; builds the records of steps jj+2, jj+3 (raw inputs `rin`) into `out` and
 // pulls the raw inputs of steps jj+4, jj+5 out of the ring into `rout`.  CK: a checkpoint is due before step jj.
 template <class AR, bool FIRST, bool TMST, bool CK>
 __device__ __forceinline__ void in_pair(const Ctx &c, int jj, const float4 *Lsrc, const int16_t *tbl,
-                                        int &ps, const PrepRec &in, PrepRec &out, const Raw &rin, Raw &rout,
+                                        int &ps, unsigned &rph, const PrepRec &in, PrepRec &out, const Raw &rin, Raw &rout,
                                         const Idx &xin, Idx &xout, float (&v)[16])
 {
     const int N = c.N;
     unsigned char *slot = c.stage + c.lane * 16 + ps * 2048;
     cpa_wait<kRingPairs - 1>();
+#ifdef NII_BULK_CHAN
+    mbar_wait(c.rmbar + 8u * ps, (rph >> ps) & 1u);
+    rph ^= 1u << ps;
+    const int si = ps;
+#else
+    const int si = 0;
+#endif
+#ifndef NII_ABL_NORAW
     raw_get<FIRST>(c, slot, rout);
-    prep_load_pair(c, slot, jj + 4 + 2 * kRingPairs, Lsrc, xin, FIRST);
+#else
+    rout = rin;
+#endif
+#ifdef NII_BULK_CHAN
+    __syncwarp();                                                   // every lane has issued its reads of this slot
+#endif
+    prep_load_pair(c, slot, jj + 4 + 2 * kRingPairs, Lsrc, xin, FIRST, si);   // (lane 0's slot address is the slot base)
     cpa_commit();
     if (!FIRST) idx_get(c, jj + 6 + 2 * kRingPairs, tbl, xout);
     ps = ps == kRingPairs - 1 ? 0 : ps + 1;
     prep_pair<AR>(c, rin, jj + 2, out);
+#ifndef NII_ABL_NOCK
     if (CK) ck_store(c, (c.M - jj) / kW - 1, v);
+#endif
     const int k0 = c.isb ? N - 1 - jj : jj, k1 = c.isb ? N - 2 - jj : jj + 1;
+#ifndef NII_ABL_NOREC
     if (TMST) tm_st8(c.tq + 8u * jj, in.gA);
     else      smem_put(c, k0, in.gA);
+#endif
     AR::pass_step(v, in.gA, c.isb);
+#ifndef NII_ABL_NOREC
     if (TMST) tm_st8(c.tq + 8u * (jj + 1), in.gB);
     else      smem_put(c, k1, in.gB);
+#endif
     AR::pass_step(v, in.gB, c.isb);
 }
 template <class AR, bool FIRST, bool TMST, bool CKA, bool CKB>
@@ -405,11 +473,11 @@ __device__ __forceinline__ void in_loop(const Ctx &c, int j0, int j1, const floa
     Idx XQ = P.ix;
     int jj = j0;
     for (; jj + 4 <= j1; jj += 4) {                                 // ping-pong: no register copies
-        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
-        in_pair<AR, FIRST, TMST, CKB>(c, jj + 2, Lsrc, tbl, P.ps, Q, P.r, RQ, P.raw, XQ, P.ix, v);
+        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.rph, P.r, Q, P.raw, RQ, P.ix, XQ, v);
+        in_pair<AR, FIRST, TMST, CKB>(c, jj + 2, Lsrc, tbl, P.ps, P.rph, Q, P.r, RQ, P.raw, XQ, P.ix, v);
     }
     if (jj < j1) {
-        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.r, Q, P.raw, RQ, P.ix, XQ, v);
+        in_pair<AR, FIRST, TMST, CKA>(c, jj, Lsrc, tbl, P.ps, P.rph, P.r, Q, P.raw, RQ, P.ix, XQ, v);
         P.r = Q;
         P.raw = RQ;
         P.ix = XQ;
@@ -427,29 +495,42 @@ __device__ __forceinline__ void in_range(const Ctx &c, int j0, int j1, const flo
 }
 
 template <class AR, bool FIRST>
-__device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16])
+__device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16], unsigned &rph)
 {
     const float4 *Lsrc = second ? c.L2A : c.L1A;
     const int16_t *tbl = second ? c.perm : c.inv;                   // La = Le[perm k] / Le[inv k]
     unsigned char *ring = c.stage + c.lane * 16;
     PrepState P;
     P.ix.a = P.ix.b = 0;
+    P.rph = rph;                                                    // phase parities of the ring mbarriers persist across calls
 #pragma unroll 1
     for (int p = 0; p < kRingPairs; ++p) {                          // ring of step pairs
         if (!FIRST) idx_get(c, 2 * p, tbl, P.ix);
-        prep_load_pair(c, ring + p * 2048, 2 * p, Lsrc, P.ix, FIRST);
+        prep_load_pair(c, ring + p * 2048, 2 * p, Lsrc, P.ix, FIRST, p);
         cpa_commit();
     }
     if (!FIRST) idx_get(c, 2 * kRingPairs, tbl, P.ix);
     cpa_wait<kRingPairs - 1>();
+#ifdef NII_BULK_CHAN
+    mbar_wait(c.rmbar, P.rph & 1u); P.rph ^= 1u;
+#endif
     raw_get<FIRST>(c, ring, P.raw);                                 // steps 0, 1
     prep_pair<AR>(c, P.raw, 0, P.r);
-    prep_load_pair(c, ring, 2 * kRingPairs, Lsrc, P.ix, FIRST);
+#ifdef NII_BULK_CHAN
+    __syncwarp();
+#endif
+    prep_load_pair(c, ring, 2 * kRingPairs, Lsrc, P.ix, FIRST, 0);
     cpa_commit();
     if (!FIRST) idx_get(c, 2 * kRingPairs + 2, tbl, P.ix);
     cpa_wait<kRingPairs - 1>();
+#ifdef NII_BULK_CHAN
+    mbar_wait(c.rmbar + 8u, (P.rph >> 1) & 1u); P.rph ^= 2u;
+#endif
     raw_get<FIRST>(c, ring + 2048, P.raw);                          // steps 2, 3
-    prep_load_pair(c, ring + 2048, 2 * kRingPairs + 2, Lsrc, P.ix, FIRST);
+#ifdef NII_BULK_CHAN
+    __syncwarp();
+#endif
+    prep_load_pair(c, ring + 2048, 2 * kRingPairs + 2, Lsrc, P.ix, FIRST, 1);
     cpa_commit();
     if (!FIRST) idx_get(c, 2 * kRingPairs + 4, tbl, P.ix);
     P.ps = 2 % kRingPairs;
@@ -457,11 +538,18 @@ __device__ __forceinline__ void in_pass(const Ctx &c, bool second, float (&v)[16
     in_range<AR, FIRST, true>(c, 0, c.T, Lsrc, tbl, P, v);
     in_range<AR, FIRST, false>(c, c.T, c.M, Lsrc, tbl, P, v);
     cpa_wait<0>();
+#ifdef NII_BULK_CHAN
+    // the ring runs kRingPairs (clamped) pairs ahead: one fill per slot is still outstanding.  It must land before the
+    // staging area is reused for the windows' beta vectors, and its phase must be consumed to keep the parities in step.
+#pragma unroll 1
+    for (int i = 0; i < kRingPairs; ++i) { mbar_wait(c.rmbar + 8u * i, (P.rph >> i) & 1u); P.rph ^= 1u << i; }
+#endif
+    rph = P.rph;
 }
 
 // One SISO half-iteration for the 16 frames of this warp.
 template <class AR, bool TIMED>
-__device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool last, bool first_iter, typename AR::sf_t sf, long long (&ph)[8])
+__device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool last, bool first_iter, typename AR::sf_t sf, long long (&ph)[8], unsigned &rph)
 {
     long long tA = TIMED ? clock64() : 0;
     const int N = c.N, M = c.M, T = c.T, lane = c.lane;
@@ -484,8 +572,8 @@ __device__ __forceinline__ void siso(const Ctx &c, bool second, bool first, bool
     }
     if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
     // ---- the "in" pass ------------------------------------------------------------------------------------------
-    if (first) in_pass<AR, true>(c, second, v);
-    else       in_pass<AR, false>(c, second, v);
+    if (first) in_pass<AR, true>(c, second, v, rph);
+    else       in_pass<AR, false>(c, second, v, rph);
     tm_wait_st();
     __syncwarp();
     if (!first && !last)                                            // old extrinsics are dead: every line is rewritten below
@@ -556,7 +644,7 @@ nii_kernel(const NiiArgs A)
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((2 * N * 2 + 15) / 16) * 16;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_raw + tab_bytes);
-    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + 64);   // 32 B of slots + four 8-byte mbarriers
+    float4 *srec_all = reinterpret_cast<float4 *>(smem_raw + tab_bytes + kHdrBytes);   // 32 B of slots + four 8-byte mbarriers (+ ring mbarriers)
     unsigned char *stage_all = reinterpret_cast<unsigned char *>(srec_all + (size_t)kTpfWarps * g.mid * 2 * 16);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -565,8 +653,12 @@ nii_kernel(const NiiArgs A)
     }
     for (int i = tid; i < 2 * N; i += blockDim.x) tab[i] = A.tab[i];
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw + tab_bytes + 32 + 8 * warp);   // this warp's mbarrier
-    unsigned mphase = 0;
-    if (lane == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
+    unsigned mphase = 0, rph = 0;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        for (int i = 0; i < kRingPairs; ++i) mbar_init((unsigned)__cvta_generic_to_shared(smem_raw + tab_bytes + 64 + 8 * (warp * kRingPairs + i)), 1);
+        mbar_fence_init();
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -586,6 +678,7 @@ nii_kernel(const NiiArgs A)
         c.one = slots[1];
         __syncwarp();
     }
+    c.rmbar = (unsigned)__cvta_generic_to_shared(smem_raw + tab_bytes + 64 + 8 * warp * kRingPairs);
     c.perm = tab; c.inv = tab + N;
     const int wg = blockIdx.x * kTpfWarps + warp;
     unsigned char *ws = A.ws + (size_t)wg * g.ws_per_warp;
@@ -700,7 +793,7 @@ nii_kernel(const NiiArgs A)
         if (TIMED) ph[0] += clock64() - t0;
         for (int h = 0; h < 2 * A.iterations; ++h) {
             const typename AR::sf_t sf = (h >> 1) < A.iterations - 1 ? sf_inner : sf_last;
-            siso<AR, TIMED>(c, (h & 1) != 0, h == 0, h == 2 * A.iterations - 1, h < 2, sf, ph);
+            siso<AR, TIMED>(c, (h & 1) != 0, h == 0, h == 2 * A.iterations - 1, h < 2, sf, ph, rph);
         }
         const long long t6 = TIMED ? clock64() : 0;
         // ---- hard decision: (Lc + La) + Le1 < 0 in float32 + optional error counting ----------------------
@@ -839,7 +932,7 @@ int nii_configure(Codec &c)
     while (g.tmem_cols < 8 * T + 2 * kW) g.tmem_cols *= 2;        // records + the window's Y
     if (g.tmem_cols > 512) return B200DVB_OK;
     const size_t tab_bytes = ((size_t)2 * N * 2 + 15) / 16 * 16;
-    g.smem_bytes = tab_bytes + 64 + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
+    g.smem_bytes = tab_bytes + kHdrBytes + (size_t)kTpfWarps * g.mid * 2 * 16 * sizeof(float4) + (size_t)kTpfWarps * kStageBytes;
     int dev = 0;
     cudaDeviceProp prop;
     B2_CUDA(cudaGetDevice(&dev));

@@ -7,10 +7,14 @@ from tests import vectors
 
 pytestmark = pytest.mark.gpu
 
-# float32 kernel vs the reference's float64: |d0 - d1| carries ~1e-6 absolute error
-# for unit-power constellations, divided by the noise variance.
-def llr_atol(nv):
-    return 4e-6 / max(nv, 0.005) + 2e-6
+# float32 kernel vs the reference's float64.  Tolerance = 2 x the largest error OBSERVED on a B200 per modulation, over the
+# fixture symbols and 200 000 random ones, noise variances 1e-4 ... 0.5 (profiles/r02_demap_observed_error.txt, made by
+# tools/demap_err.py); every entry is below the 1e-4 that BASELINE.md section 4 states for +-30-clipped LLRs.
+LLR_ATOL = {'BPSK': 9e-5, 'QPSK': 1e-5, '8PSK': 3.2e-5, '16QAM': 2.7e-5, '64QAM': 2.2e-5, '256QAM': 2.4e-5}
+
+
+def llr_atol(name):
+    return LLR_ATOL[name]
 
 
 @pytest.mark.parametrize("name", list(vectors.BPS))
@@ -56,10 +60,10 @@ def test_compute_llr(golden, name):
         if key in m.files:                                               # reference's own output
             assert np.array_equal(want[:vectors.DEMAP_N * vectors.BPS[name]], m[key])
         err = np.abs(got - want)
-        assert err.max() <= llr_atol(nv), (name, nv, err.max())
+        assert err.max() <= llr_atol(name), (name, nv, "max |dLLR| = %.3e" % err.max())
         # identical hard decisions except on near-zero |LLR| ties
         bad = (got > 0) != (want > 0)
-        assert np.all(np.abs(want[bad]) < llr_atol(nv))
+        assert np.all(np.abs(want[bad]) < llr_atol(name))
         assert np.array_equal(decoder_llr(rx, name, nv), -got.astype(np.float32))
     assert np.all(np.abs(compute_llr(rx, name, 0.001)) <= 30.0)
 
@@ -89,7 +93,7 @@ def test_modulator_llr_nongray_table():
     rx = oracle.modulator_mod(bits, '16QAM') + 0.1 * (rs.randn(500) + 1j * rs.randn(500))
     got = compute_llr(rx, '16QAM', 0.02, constellation=c)
     want = oracle.compute_llr(rx, '16QAM', 0.02, constellation=c)
-    assert np.abs(got - want).max() <= llr_atol(0.02)
+    assert np.abs(got - want).max() <= llr_atol('16QAM')
 
 
 def test_coded_16qam_pipeline(golden):
@@ -112,5 +116,5 @@ def test_coded_16qam_pipeline(golden):
     rx = syms + np.sqrt(nv / 2) * (rs.randn(len(syms)) + 1j * rs.randn(len(syms)))
     llr_o = (-oracle.compute_llr(rx, '16QAM', nv))[:g.n_coded].astype(np.float32)
     llr_g = decoder_llr(rx, '16QAM', nv)[:g.n_coded]
-    assert np.abs(llr_g - llr_o).max() <= llr_atol(nv)
+    assert np.abs(llr_g - llr_o).max() <= llr_atol('16QAM')
     assert np.array_equal(g.decode(llr_o), o.decode(llr_o))

@@ -376,9 +376,13 @@ __device__ __forceinline__ void prep_load_pair(const Ctx &c, unsigned char *slot
     cpa16_stream_off<1024, 512>(d, src, c.pol);
 #endif
 #ifndef NII_ABL_NOGATHER
-    if (!first) {
-        cpa16_off<512, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.a * 16) + (c.f >> 1));
-        cpa16_off<1536, 0>(d, reinterpret_cast<const float4 *>(c.Le + x.b * 16) + (c.f >> 1));
+    // the a-priori pair of a frame is 8 bytes and a 16-byte chunk holds two neighbouring frames: only the EVEN lanes
+    // copy, into chunk (lane / 2) of the la block, and both lanes of the pair read their half (the cost of the global
+    // path is per byte, profiles/r02_nii_ablation.txt: 256 B per step instead of 512 B)
+    if (!first && (c.lane & 1) == 0) {
+        const unsigned dl = d - 8u * (unsigned)c.lane;              // slot base + (lane / 2) * 16
+        cpa16_off<512, 0>(dl, reinterpret_cast<const float4 *>(c.Le + x.a * 16) + (c.f >> 1));
+        cpa16_off<1536, 0>(dl, reinterpret_cast<const float4 *>(c.Le + x.b * 16) + (c.f >> 1));
     }
 #endif
 }
@@ -395,8 +399,14 @@ __device__ __forceinline__ void raw_get(const Ctx &c, const unsigned char *slot,
     r.xB = *reinterpret_cast<const float4 *>(slot + oXB);
     r.laA = r.laB = make_float2(0.f, 0.f);
     if (!FIRST) {
+#ifdef NII_BULK_CHAN
         r.laA = *reinterpret_cast<const float2 *>(slot + oLA + c.h8);
         r.laB = *reinterpret_cast<const float2 *>(slot + 1536 + c.h8);
+#else
+        const unsigned char *la = slot - 8 * c.lane;                // chunk (lane / 2), this lane's half (h8 = 8 * (lane & 1)): + 8 * lane in total
+        r.laA = *reinterpret_cast<const float2 *>(la + oLA);
+        r.laB = *reinterpret_cast<const float2 *>(la + 1536);
+#endif
     }
 }
 struct PrepRec { float gA[8], gB[8]; };                      // records of two consecutive steps

@@ -94,9 +94,11 @@ def test_nii_ber_inside_parity_confidence_interval(mode):
     (normal approximation, 2.576 sigma of the pooled estimate) of the other's.  (The frames are the same, so the
     two estimates are positively correlated and the test is conservative in the right direction: a real difference
     larger than the interval of INDEPENDENT samples fails.)  The fixed-point mode additionally gets a stated
-    quantisation allowance of 1 % RELATIVE (LLRs in 1/4 units, 9-bit extrinsics): with 55 M bits per point the
-    binomial interval is 0.17 % of the BER at 2 dB and resolves the format's real cost (measured: +0.29 % of the BER at
-    2 dB, i.e. a few thousandths of a dB; profiles/r02_ber_three_modes.txt)."""
+    quantisation allowance: 1 % of the BER and 4 % of the FER, RELATIVE.  With 55 M bits per point the binomial
+    interval is 0.17 % of the BER at 2 dB and resolves the format's real cost: +0.3 ... +0.7 % of the BER and +1 ... +3 % of
+    the FER in the waterfall (a few hundredths of a dB; profiles/r02_ber_three_modes.txt).  The clamps play no part in
+    it (the C model gives identical decisions with wider ones); it is the 1/4-LLR resolution: a-posteriori values that
+    come out EXACTLY zero are decided arbitrarily, which a float decoder never sees."""
     import torch
     from modulations_b200 import dvb_rcs2_turbo as turbo
     N, rate, B = 212, '1/3', 1 << 17
@@ -119,7 +121,7 @@ def test_nii_ber_inside_parity_confidence_interval(mode):
             p = (e0 + e1) / (2 * n)
             half = 2.576 * np.sqrt(max(p * (1 - p), 1e-12) * 2 / n)
             if mode == "nii16":
-                half = max(half, 0.01 * e0 / n)
+                half = max(half, (0.01 if what == "BER" else 0.04) * e0 / n)
             assert abs(e0 / n - e1 / n) <= half + 1e-12, (ebn0, what, e0 / n, e1 / n, half)
 
 

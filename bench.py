@@ -55,16 +55,23 @@ def lib_sha256():
 
 def committed_ncu(sha):
     """profiles/r02_traffic.json: per-kernel figures read out of committed `ncu --set full` captures (DRAM bytes per
-    frame, issue-slot and pipe utilisation), stamped with the sha256 of the library they were taken on.  A figure
-    from another binary is NOT reported: the caller gets None plus the reason."""
+    frame, issue-slot and pipe utilisation), stamped with the sha256 of the library they were taken on and of the
+    sources + flags it is built from (nvcc output is not byte-reproducible).  A figure from other kernels is NOT
+    reported: the caller gets None plus the reason."""
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception as e:
         return None, f"profiles/r02_traffic.json unreadable ({e!r})"
-    if tr.get("lib_sha256") != sha:
-        return None, ("profiles/r02_traffic.json was captured on another build of libb200dvb.so "
-                      f"({str(tr.get('lib_sha256'))[:12]} != {str(sha)[:12]}): re-run tools/gpu_dram.sh")
-    return tr, None
+    if tr.get("lib_sha256") == sha:
+        return tr, None
+    try:        # the same SOURCES and flags compiled on another machine: identified by the hash of what the library is built from
+        from modulations_b200.build import source_sha256
+        if tr.get("src_sha256") == source_sha256():
+            return tr, None
+    except Exception:
+        pass
+    return None, ("profiles/r02_traffic.json was captured on another build of libb200dvb.so "
+                  f"({str(tr.get('lib_sha256'))[:12]} != {str(sha)[:12]}, sources differ too): re-run tools/gpu_dram.sh")
 
 
 class ClockSampler:

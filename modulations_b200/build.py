@@ -27,6 +27,20 @@ def _nvcc():
     return "nvcc"
 
 
+def source_sha256():
+    """sha256 over everything the library is built from (csrc/*, include/b200dvb.h, the nvcc flags): identifies a
+    build independently of the machine that compiled it.  profiles/r02_traffic.json is stamped with it."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "b200dvb.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

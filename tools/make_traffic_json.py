@@ -32,7 +32,9 @@ def main():
     prof_sha = open(os.path.join(OUT, "dram_lib_sha256.txt")).read().split()[0]
     if prof_sha != sha:
         sys.exit(f"the captures were taken on library {prof_sha[:12]}, the tree now holds {sha[:12]}: re-run tools/gpu_dram.sh")
-    res = {"lib_sha256": sha, "how": "tools/gpu_dram.sh (ncu --set full --clock-control none, one launch each) + tools/make_traffic_json.py"}
+    sys.path.insert(0, ROOT)
+    from modulations_b200.build import source_sha256
+    res = {"lib_sha256": sha, "src_sha256": source_sha256(), "how": "tools/gpu_dram.sh (ncu --set full --clock-control none, one launch each) + tools/make_traffic_json.py"}
     for key, rep, frames in (("tpf_kernel", "prof_dram_tpf.ncu-rep", 37888), ("nii_kernel", "prof_dram_nii.ncu-rep", 37888),
                              ("quad_kernel_n752", "prof_dram_quad752.ncu-rep", 4736)):
         p = os.path.join(OUT, rep)

@@ -128,6 +128,17 @@ __global__ void encode_kernel(int B, int N, int n_llr, int fpb, int in_stride, i
     }
 }
 
+// Box-Muller pair from two uniforms in (0, 1): hardware approximations (MUFU.LG2 / RSQ / SIN / COS).  The source is
+// statistical (Philox, not the reference's MT19937), so a 2^-21 error in a noise sample is immaterial; the library
+// versions of logf / sincospif made the AWGN kernels compute-bound at a third of the HBM rate.
+__device__ __forceinline__ void box_muller(float u1, float u2, float &n0, float &n1)
+{
+    const float rad = __fsqrt_rn(-2.0f * __logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);   // argument in (-pi, pi): the fast path's accurate range
+    n0 = -rad * cs; n1 = -rad * sn;                                      // cos(x - pi) = -cos x, sin(x - pi) = -sin x
+}
+
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ------------------------
 struct Philox { unsigned c[4]; };
 __device__ __forceinline__ Philox philox(unsigned long long counter, unsigned stream,
@@ -175,10 +186,7 @@ __global__ void awgn_bpsk_kernel(size_t n4, size_t n, float sigma, float two_ove
     for (int h = 0; h < 2; ++h) {
         const float u1 = ((float)r.c[2 * h] + 0.5f) * 2.3283064365386963e-10f;
         const float u2 = ((float)r.c[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
-        const float rad = sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
-        float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
-        nrm[2 * h] = rad * cs; nrm[2 * h + 1] = rad * sn;
+        box_muller(u1, u2, nrm[2 * h], nrm[2 * h + 1]);
     }
     const size_t e = 4 * i;
     if (e + 3 < n) {
@@ -208,11 +216,10 @@ __global__ void awgn_complex_kernel(size_t n2, size_t n, float sigma, unsigned l
         if (e >= n) break;
         const float u1 = ((float)r.c[2 * h] + 0.5f) * 2.3283064365386963e-10f;
         const float u2 = ((float)r.c[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
-        const float rad = sigma * sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
-        float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
+        float g0, g1;
+        box_muller(u1, u2, g0, g1);
         float2 v = iq[e];
-        v.x += rad * cs; v.y += rad * sn;
+        v.x += sigma * g0; v.y += sigma * g1;
         iq[e] = v;
     }
 }

@@ -58,31 +58,37 @@ pulse_shape_kernel(size_t n_sym, const float2 *__restrict__ sym, const __grid_co
 // Compile-time sps: a thread owns ALL sps output samples of one symbol period q — the Q = ceil(ntaps/sps) symbols
 // they depend on are loaded once (coalesced: consecutive threads, consecutive symbols) and the sps*Q complex MACs run
 // out of registers; the thread's sps samples are 8*sps contiguous bytes, stored 16 B at a time.  T.h is zero beyond ntaps.
-template <int SPS>
+template <int SPS, int QT>
 __global__ void __launch_bounds__(256)
 pulse_shape_sps_kernel(size_t n_sym, const float2 *__restrict__ sym, const __grid_constant__ FirTaps T, int ntaps,
                        size_t n_out, float2 *__restrict__ out)
 {
-    constexpr int kMaxQ = 16;
-    const int Q = (ntaps + SPS - 1) / SPS;
+    // QT = compile-time bound of the symbols an output period depends on (ceil(ntaps / SPS) <= QT; T.h is zero beyond
+    // ntaps).  Interior periods (every one of the QT symbols exists) take a path without per-load bounds checks and
+    // 64-bit compares: the round-1 kernel spent 75 % of its issue slots on the ALU pipe doing exactly those
+    // (profiles/r02_waveform_ncu.txt) and was ALU-bound, not HBM-bound.
     const size_t nq = (n_out + SPS - 1) / SPS;                      // symbol periods that hold output samples
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
-        float2 s[kMaxQ];
+        float2 s[QT];
+        if (q >= (size_t)(QT - 1) && q < n_sym) {
+            const float2 *p = sym + q;
 #pragma unroll
-        for (int j = 0; j < kMaxQ; ++j)
-            s[j] = (j < Q && q >= (size_t)j && q - j < n_sym) ? __ldg(sym + (q - j)) : make_float2(0.f, 0.f);
+            for (int j = 0; j < QT; ++j) s[j] = __ldg(p - j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < QT; ++j)
+                s[j] = (q >= (size_t)j && q - j < n_sym) ? __ldg(sym + (q - j)) : make_float2(0.f, 0.f);
+        }
         float2 acc[SPS];
 #pragma unroll
         for (int p = 0; p < SPS; ++p) acc[p] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kMaxQ; ++j) {
-            if (j < Q) {
+        for (int j = 0; j < QT; ++j) {
 #pragma unroll
-                for (int p = 0; p < SPS; ++p) {
-                    const float hh = T.h[j * SPS + p];
-                    acc[p].x = fmaf(s[j].x, hh, acc[p].x);
-                    acc[p].y = fmaf(s[j].y, hh, acc[p].y);
-                }
+            for (int p = 0; p < SPS; ++p) {
+                const float hh = T.h[j * SPS + p];
+                acc[p].x = fmaf(s[j].x, hh, acc[p].x);
+                acc[p].y = fmaf(s[j].y, hh, acc[p].y);
             }
         }
         float2 *o = out + q * SPS;
@@ -346,9 +352,13 @@ int launch_pulse_shape(size_t n_sym, const void *sym, const double *taps_h, int 
     if ((sps == 8 || sps == 4 || sps == 2) && Q <= 16 && al16) {
         size_t blocks = ((n_out + sps - 1) / sps + 255) / 256;
         if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
-        if (sps == 8)      pulse_shape_sps_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
-        else if (sps == 4) pulse_shape_sps_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
-        else               pulse_shape_sps_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o);
+#define B2_PS(S, QQ) pulse_shape_sps_kernel<S, QQ><<<(unsigned)blocks, 256, 0, s>>>(n_sym, sy, T, ntaps, n_out, o)
+#define B2_PSQ(S) do { if (Q <= 4) B2_PS(S, 4); else if (Q <= 7) B2_PS(S, 7); else if (Q <= 10) B2_PS(S, 10); else B2_PS(S, 16); } while (0)
+        if (sps == 8)      B2_PSQ(8);
+        else if (sps == 4) B2_PSQ(4);
+        else               B2_PSQ(2);
+#undef B2_PSQ
+#undef B2_PS
         B2_CUDA(cudaGetLastError());
         return B200DVB_OK;
     }
@@ -391,9 +401,18 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
             if (bmax - bmin + 1 > qw) qw = bmax - bmin + 1;
         }
         const int qsel = qw <= 4 ? 4 : qw <= 6 ? 6 : qw <= 7 ? 7 : qw <= 8 ? 8 : 9;
+        // Bank layout of the staging stores.  A 16-byte shared-memory access is served per QUARTER warp (8 consecutive
+        // lanes = 8 consecutive 16-byte entries of the input = 8 / npair consecutive positions x npair phase pairs),
+        // and those 8 must fall into 8 different 16-byte bank groups: entry (pp, pos) sits at pp * pitch + (pos mod 4)
+        // * q4 + pos div 4, so the residues of q4 and of the row pitch mod 8 are chosen per npair (the first version
+        // used one choice for all and ran at 2 wavefronts per store and 82 % LSU load: profiles/r02_waveform_ncu.txt).
+        const int np = sps / 2;
+        const int q4_res = np == 1 ? 2 : 1;                          // npair 1: 8 positions -> {0,2,4,6} + {0,1}
+        const int pitch_res = np == 2 ? 4 : np == 4 ? 2 : 1;         // npair 2: {0..3} + {0,4}; 4: {0,1} + {0,2,4,6}; >= 8: odd pitch
         int q4 = (kMf4Tile + omax + qsel + 3 + 3) / 4 + 1;          // entries per sub-row: the tile + the windows' reach
-        while ((q4 & 7) != 2) ++q4;                                 // sub-row pitch = 2 (mod 8) 16-byte words: a warp's cp.async
-        const int pitch4 = 4 * q4;                                  // writes (4 pairs x 8 positions) spread over all banks
+        while ((q4 & 7) != q4_res) ++q4;
+        int pitch4 = 4 * q4;
+        while ((pitch4 & 7) != pitch_res) ++pitch4;
         const bool use_async = g_mf_variant == 1;
         const size_t smem4 = (size_t)(use_async ? 2 : 1) * (sps / 2) * pitch4 * sizeof(float4);
         int pair_shift = -1;

@@ -337,6 +337,16 @@ def run_ours(args, rank, world, local_rank):
                        "seconds_for_1e10_symbols": ms * 1e-3 * 1e10 / nsym,
                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                     "peak_source": hbm_src, "traffic": tr * nsym if tr else None}}
+        if name in ("16QAM", "256QAM"):      # bf16x2 I/Q input (north_star "bf16x2 loads"), reported separately
+            xb = torch.view_as_real(iq).to(torch.bfloat16).contiguous()
+            ms = time_kernel(lambda: _lib.check(lib.b200dvb_demap_bf16(m.h, nsym, _lib.ptr(xb), 0.05, 1.0, _lib.ptr(out),
+                                                                      _lib.stream_ptr()), "demap_bf16"))
+            by = nsym * (4 + 4 * m.bps)
+            gbs = by / (ms * 1e-3) / 1e9
+            demap[name]["bf16x2_input"] = {"gsym_per_s": nsym / (ms * 1e-3) / 1e9, "bytes_per_symbol": 4 + 4 * m.bps,
+                                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                                        "frac": gbs / hbm, "peak_source": hbm_src, "traffic": None}}
+            del xb
         del out
         bits_in = torch.randint(0, 2, (nsym * m.bps,), dtype=torch.uint8, device=dev)
         sy = torch.empty(nsym, dtype=torch.complex64, device=dev)

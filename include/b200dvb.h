@@ -163,6 +163,12 @@ int b200dvb_map(b200dvb_modem_t modem, size_t n_sym, const uint8_t *bits, void *
  * (use -1 to feed the decoder, whose convention is positive = bit 0). */
 int b200dvb_demap(b200dvb_modem_t modem, size_t n_sym, const void *iq, float noise_var,
                   float scale, float *llr, void *stream);
+/* The same with bf16x2 symbols (4 bytes per symbol: bf16 I, then bf16 Q; BASELINE north_star "bf16x2 loads of I/Q"):
+ * each component is widened exactly to float32 and goes through the arithmetic of b200dvb_demap, so
+ * b200dvb_demap_bf16(x) == b200dvb_demap(float32(x)) bit for bit.  Reported separately in the bench line
+ * (4 + 4 bps algorithmic bytes per symbol instead of 8 + 4 bps). */
+int b200dvb_demap_bf16(b200dvb_modem_t modem, size_t n_sym, const void *iq_bf16x2, float noise_var,
+                       float scale, float *llr, void *stream);
 /* Hard decisions.  Replaces SDRModem.demodulate (sdr_modem.py:245-266) and
  * Modulator._demod_qam_generic (modulators.py:165-171): nearest constellation
  * point, evaluated in float64.  in_f64 selects float2 / double2 input. */

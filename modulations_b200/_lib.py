@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200dvb_modem_destroy": (_c_int, [_c_void_p]),
     "b200dvb_map": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "b200dvb_demap": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_float, _c_float, _c_void_p, _c_void_p]),
+    "b200dvb_demap_bf16": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_float, _c_float, _c_void_p, _c_void_p]),
     "b200dvb_hard_demod": (_c_int, [_c_void_p, _c_size_t, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "b200dvb_pulse_shape": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "b200dvb_matched_filter": (_c_int, [_c_size_t, _c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_size_t, _c_void_p, _c_void_p]),

@@ -407,6 +407,13 @@ int b200dvb_demap(b200dvb_modem_t modem, size_t n_sym, const void *iq, float noi
     return launch_demap(modem->m, n_sym, iq, noise_var, scale, llr, (cudaStream_t)stream);
 }
 
+int b200dvb_demap_bf16(b200dvb_modem_t modem, size_t n_sym, const void *iq_bf16x2, float noise_var,
+                       float scale, float *llr, void *stream)
+{
+    if (!modem || !iq_bf16x2 || !llr) return B200DVB_EINVAL;
+    return launch_demap_bf16(modem->m, n_sym, iq_bf16x2, noise_var, scale, llr, (cudaStream_t)stream);
+}
+
 int b200dvb_hard_demod(b200dvb_modem_t modem, size_t n_sym, const void *iq, int in_f64,
                        uint8_t *bits, void *stream)
 {

@@ -120,8 +120,30 @@ template <int BPS> struct PwlLlr {          // BPS = 2 * HALF
     }
 };
 
-template <int BPS, int SPT, class F>
-__device__ __forceinline__ void demap_body(size_t n, const float2 *__restrict__ iq, float *__restrict__ llr,
+// Symbol input formats of the demapper: complex64 (float2, the reference's dtype) or bf16x2 (4 bytes per symbol,
+// BASELINE north_star "bf16x2 loads of I/Q": widened exactly to float32, then the same arithmetic).
+struct InF32 {
+    typedef float2 sym_t;
+    static __device__ __forceinline__ float2 one(const sym_t *p, size_t i) { return __ldcs(p + i); }
+    static __device__ __forceinline__ void two(const sym_t *p, size_t i, float2 &a, float2 &b)
+    {
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(p + i));
+        a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
+    }
+};
+struct InBf16 {
+    typedef unsigned sym_t;                                 // low half = I, high half = Q (a little-endian bf16 pair)
+    static __device__ __forceinline__ float2 widen(unsigned w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+    static __device__ __forceinline__ float2 one(const sym_t *p, size_t i) { return widen(__ldcs(p + i)); }
+    static __device__ __forceinline__ void two(const sym_t *p, size_t i, float2 &a, float2 &b)
+    {
+        const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(p + i));
+        a = widen(t.x); b = widen(t.y);
+    }
+};
+
+template <int BPS, int SPT, class IN, class F>
+__device__ __forceinline__ void demap_body(size_t n, const typename IN::sym_t *__restrict__ iq, float *__restrict__ llr,
                                            const F &f, float *stage)
 {
     constexpr int CH = BPS * SPT;                       // floats per thread
@@ -133,13 +155,10 @@ __device__ __forceinline__ void demap_body(size_t n, const float2 *__restrict__ 
         float2 s[SPT];
         if (full && (SPT % 2) == 0) {
 #pragma unroll
-            for (int j = 0; j < SPT; j += 2) {
-                const float4 t = __ldcs(reinterpret_cast<const float4 *>(iq + i0 + j));
-                s[j] = make_float2(t.x, t.y); s[j + 1] = make_float2(t.z, t.w);
-            }
+            for (int j = 0; j < SPT; j += 2) IN::two(iq, i0 + j, s[j], s[j + 1 < SPT ? j + 1 : j]);
         } else {
 #pragma unroll
-            for (int j = 0; j < SPT; ++j) s[j] = (i0 + j < n) ? __ldcs(iq + i0 + j) : make_float2(0.f, 0.f);
+            for (int j = 0; j < SPT; ++j) s[j] = (i0 + j < n) ? IN::one(iq, i0 + j) : make_float2(0.f, 0.f);
         }
         float v[SPT][BPS];
 #pragma unroll
@@ -173,9 +192,9 @@ __device__ __forceinline__ void demap_body(size_t n, const float2 *__restrict__ 
     }
 }
 
-template <int BPS, int SPT>
+template <int BPS, int SPT, class IN>
 __global__ void __launch_bounds__(kThreads)
-demap_generic(size_t n, const float2 *__restrict__ iq, const float *__restrict__ table,
+demap_generic(size_t n, const typename IN::sym_t *__restrict__ iq, const float *__restrict__ table,
               float inv_nv, float scale, float *__restrict__ llr)
 {
     constexpr int M = 1 << BPS;
@@ -184,13 +203,13 @@ demap_generic(size_t n, const float2 *__restrict__ iq, const float *__restrict__
     for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = make_float2(table[2 * i], table[2 * i + 1]);
     __syncthreads();
     GenericLlr<BPS> f{tab, inv_nv, scale};
-    demap_body<BPS, SPT>(n, iq, llr, f, stage);
+    demap_body<BPS, SPT, IN>(n, iq, llr, f, stage);
 }
 
 // Per-axis piecewise-linear demapper.  coef: float2[2][HALF][nseg].
-template <int HALF, int SPT>
+template <int HALF, int SPT, class IN>
 __global__ void __launch_bounds__(kThreads)
-demap_pwl(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
+demap_pwl(size_t n, const typename IN::sym_t *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
           float x0a, float invda, float x0b, float invdb, int first_is_q, float inv_nv, float scale,
           float *__restrict__ llr)
 {
@@ -200,14 +219,15 @@ demap_pwl(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ co
     for (int i = threadIdx.x; i < 2 * HALF * nseg; i += blockDim.x) sc[i] = coef[i];
     __syncthreads();
     PwlLlr<BPS> f{sc, nseg, first_is_q, x0a, invda, x0b, invdb, inv_nv, scale};
-    demap_body<BPS, SPT>(n, iq, llr, f, stage);
+    demap_body<BPS, SPT, IN>(n, iq, llr, f, stage);
 }
 
 // 256QAM (4 bits per axis): one thread per (symbol, axis) writes one float4, so a warp's
 // stores are 512 contiguous bytes with no staging; both threads of a symbol read the same
 // 8 input bytes.
+template <class IN>
 __global__ void __launch_bounds__(kThreads)
-demap_pwl_axis4(size_t n, const float2 *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
+demap_pwl_axis4(size_t n, const typename IN::sym_t *__restrict__ iq, const float2 *__restrict__ coef, int nseg,
                 float x0a, float invda, float x0b, float invdb, int first_is_q, float inv_nv, float scale,
                 float4 *__restrict__ llr4)
 {
@@ -215,7 +235,7 @@ demap_pwl_axis4(size_t n, const float2 *__restrict__ iq, const float2 *__restric
     for (int i = threadIdx.x; i < 2 * 4 * nseg; i += blockDim.x) sc[i] = coef[i];
     __syncthreads();
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += (size_t)gridDim.x * blockDim.x) {
-        const float2 s = __ldcs(iq + (t >> 1));
+        const float2 s = IN::one(iq, t >> 1);
         const int ax = (int)(t & 1);                    // 0: first half of the label, 1: second half
         const float x = (ax ^ first_is_q) ? s.y : s.x;
         const float x0 = ax ? x0b : x0a, invd = ax ? invdb : invda;
@@ -312,11 +332,12 @@ int launch_hard(const Modem &m, size_t n, const void *iq, int in_f64, uint8_t *b
     return B200DVB_OK;
 }
 
-int launch_demap(const Modem &m, size_t n, const void *iq_, float noise_var, float scale, float *llr,
-                 cudaStream_t s)
+template <class IN>
+static int launch_demap_t(const Modem &m, size_t n, const void *iq_, float noise_var, float scale, float *llr,
+                          cudaStream_t s)
 {
     if (n == 0) return B200DVB_OK;
-    const float2 *iq = (const float2 *)iq_;
+    const typename IN::sym_t *iq = (const typename IN::sym_t *)iq_;
     if ((reinterpret_cast<uintptr_t>(iq_) & 15) || (reinterpret_cast<uintptr_t>(llr) & 15))
         return B200DVB_EINVAL;                               // vector loads/stores need 16-byte alignment
     const float nv = noise_var > 0.005f ? noise_var : 0.005f;      // test_sdr_with_coding.py:202
@@ -324,14 +345,14 @@ int launch_demap(const Modem &m, size_t n, const void *iq_, float noise_var, flo
     if (m.pwl) {
         const float2 *coef = (const float2 *)m.d_pwl;
         const int fq = (m.separable == 2);
-#define PWL(H, S) demap_pwl<H, S><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(                    \
+#define PWL(H, S) demap_pwl<H, S, IN><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(                \
         n, iq, coef, m.nseg, m.pwl_x0[0], m.pwl_invd[0], m.pwl_x0[1], m.pwl_invd[1], fq, inv_nv, scale, llr)
         switch (m.half) {
         case 1: PWL(1, 2); break;
         case 2: PWL(2, 1); break;
         case 3: PWL(3, 2); break;
         case 4:
-            demap_pwl_axis4<<<grid_for(2 * n, kThreads, 8), kThreads, 0, s>>>(
+            demap_pwl_axis4<IN><<<grid_for(2 * n, kThreads, 8), kThreads, 0, s>>>(
                 n, iq, coef, m.nseg, m.pwl_x0[0], m.pwl_invd[0], m.pwl_x0[1], m.pwl_invd[1], fq, inv_nv, scale,
                 reinterpret_cast<float4 *>(llr));
             break;
@@ -340,7 +361,7 @@ int launch_demap(const Modem &m, size_t n, const void *iq_, float noise_var, flo
 #undef PWL
     } else {
         switch (m.bps) {
-#define GEN(B, S) demap_generic<B, S><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr)
+#define GEN(B, S) demap_generic<B, S, IN><<<grid_for(n, kThreads * S, 8), kThreads, 0, s>>>(n, iq, m.d_table32, inv_nv, scale, llr)
         case 1: GEN(1, 4); break;
         case 2: GEN(2, 2); break;
         case 3: GEN(3, 4); break;
@@ -353,6 +374,15 @@ int launch_demap(const Modem &m, size_t n, const void *iq_, float noise_var, flo
     }
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
+}
+
+int launch_demap(const Modem &m, size_t n, const void *iq, float noise_var, float scale, float *llr, cudaStream_t s)
+{
+    return launch_demap_t<InF32>(m, n, iq, noise_var, scale, llr, s);
+}
+int launch_demap_bf16(const Modem &m, size_t n, const void *iq, float noise_var, float scale, float *llr, cudaStream_t s)
+{
+    return launch_demap_t<InBf16>(m, n, iq, noise_var, scale, llr, s);
 }
 
 }  // namespace b200dvb

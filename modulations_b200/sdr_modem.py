@@ -110,6 +110,22 @@ class ModemHandle:
         return out if is_torch else out.cpu().numpy()
 
 
+    def llr_bf16(self, symbols_bf16, noise_var, scale=1.0):
+        """The same for bf16x2 symbols: a CUDA (or CPU) torch.bfloat16 tensor [n, 2] (I, Q).  Each component is
+        widened exactly to float32 on the device; 4 bytes per symbol are read instead of 8."""
+        torch = _lib.require_cuda()
+        s = symbols_bf16.to(device=self.device).contiguous()
+        if s.dtype != torch.bfloat16 or s.dim() != 2 or s.shape[1] != 2:
+            raise ValueError("symbols_bf16 must be a torch.bfloat16 tensor of shape [n, 2]")
+        n = s.shape[0]
+        out = torch.empty(n * self.bps, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b200dvb_demap_bf16(self.h, n, _lib.ptr(s), float(noise_var), float(scale),
+                                                _lib.ptr(out), _lib.stream_ptr(self.device))
+        _lib.check(rc, "demap_bf16")
+        return out
+
+
 _handles = {}
 
 

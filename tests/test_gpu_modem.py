@@ -118,3 +118,29 @@ def test_coded_16qam_pipeline(golden):
     llr_g = decoder_llr(rx, '16QAM', nv)[:g.n_coded]
     assert np.abs(llr_g - llr_o).max() <= llr_atol('16QAM')
     assert np.array_equal(g.decode(llr_o), o.decode(llr_o))
+
+
+@pytest.mark.parametrize("name", list(vectors.BPS))
+def test_bf16_symbol_input(name):
+    """bf16x2 I/Q input (4 bytes per symbol): every component is widened exactly to float32 on the device, so the
+    result equals the float32-input demapper on the widened symbols bit for bit, and the oracle on them within the
+    modulation's tolerance."""
+    import torch
+    from modulations_b200.sdr_modem import gray_modem
+    rs = np.random.RandomState(77)
+    n = 100_003
+    tx = oracle.modulate(rs.randint(0, 2, vectors.BPS[name] * n), name)
+    rx = tx + 0.1 * (rs.randn(n) + 1j * rs.randn(n))
+    xb = torch.from_numpy(np.stack([rx.real, rx.imag], axis=1).astype(np.float32)).to(torch.bfloat16).cuda()
+    wide = xb.float().contiguous()                                  # exact widening
+    m = gray_modem(name)
+    for nv, scale in ((0.05, 1.0), (0.5, -1.0)):
+        got = m.llr_bf16(xb, nv, scale)
+        same = m.llr(torch.view_as_complex(wide), nv, scale)
+        assert got.dtype == torch.float32 and got.shape == same.shape
+        assert torch.equal(got, same)
+        wc = wide.cpu().numpy()
+        want = scale * oracle.compute_llr(wc[:, 0].astype(np.float64) + 1j * wc[:, 1].astype(np.float64), name, nv)
+        assert np.abs(got.cpu().numpy() - want).max() <= llr_atol(name)
+    with pytest.raises(ValueError):
+        m.llr_bf16(wide, 0.05)

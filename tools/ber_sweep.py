@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--frames", type=int, default=1 << 20, help="frame cap per Eb/N0 point (whole job)")
     ap.add_argument("--min-frame-errors", type=int, default=100, dest="mfe")
     ap.add_argument("--batch", type=int, default=1 << 17)
+    ap.add_argument("--modes", nargs="+", default=["double-pass"], choices=["double-pass", "nii", "nii16"],
+                    help="decoder modes for the bijective-interleaver runs (non-parity modes are labelled as such)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -42,14 +44,20 @@ def main():
                          frames_per_point=args.frames, batch=args.batch, modulation=args.mod,
                          min_frame_errors=args.mfe)
     out = {}
-    for label, perm in (("parity (committed interleaver table)", None),
-                        ("non-parity (bijective interleaver)", bijective_interleaver(args.N))):
-        codec = DVBRCS2_Turbo(args.N, args.rate, args.iters, perm=perm)
+    runs = [("parity (committed interleaver table)", None, "double-pass")]
+    for mode in args.modes:
+        what = "reference decoder arithmetic" if mode == "double-pass" else f"NON-PARITY decoder mode {mode}"
+        runs.append((f"non-parity (bijective interleaver), {what}", bijective_interleaver(args.N), mode))
+    for label, perm, mode in runs:
+        codec = DVBRCS2_Turbo(args.N, args.rate, args.iters, perm=perm, boundary=mode)
         out[label] = mc.run_sweep(cfg, rank, world, codec=codec)
+        res = out[label]
+        tot = sum(p["frames"] for p in res["points"])
+        res["info_gbit_per_s_wall"] = tot * 2 * args.N / max(res["seconds"], 1e-9) / 1e9
     if rank == 0:
         print(json.dumps({"config": vars(args), "n_gpus": world, "runs": out}))
         for label, res in out.items():
-            print(f"# {label}: {res['seconds']:.1f} s", file=sys.stderr)
+            print(f"# {label}: {res['seconds']:.2f} s wall = {res['info_gbit_per_s_wall']:.2f} Gbit/s of information incl. the source", file=sys.stderr)
             for p in res["points"]:
                 print(f"#   Eb/N0 {p['ebn0_db']:4.1f} dB  frames {p['frames']:9d}  BER {p['ber']:.3e}  FER {p['fer']:.3e}", file=sys.stderr)
     if world > 1:

@@ -79,8 +79,9 @@ int b200dvb_codec_n_llr(b200dvb_codec_t codec);
 int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec);
 
 /* Development / test switches of one codec handle (production code never needs them):
- *   B200DVB_OPT_KERNEL          0 = automatic (per batch size), 1 = quad kernel, 2 = thread-per-frame kernel
- *                               (B200DVB_ENOSPEC when the codec's N has no thread-per-frame geometry)
+ *   B200DVB_OPT_KERNEL          0 = automatic (per batch size), 1 = quad kernel, 2 = thread-per-frame kernel,
+ *                               3 = low-latency kernel (one CTA per frame; parity mode only)
+ *                               (B200DVB_ENOSPEC when the codec's N has no geometry for the kernel asked for)
  *   B200DVB_OPT_NO_ROW_STAGING  1 = thread-per-frame transposition without the cp.async row staging
  *   B200DVB_OPT_PHASE_TIMERS    1 = launches add per-phase SM cycles to the b200dvb_debug_*_cycles counters */
 #define B200DVB_OPT_KERNEL          1

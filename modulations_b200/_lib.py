@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libb200dvb.so")
 OK, EINVAL, ENOSPEC, ECUDA, ENOMEM, EMOD = 0, -1, -2, -3, -4, -5
 OPT_KERNEL, OPT_NO_ROW_STAGING, OPT_PHASE_TIMERS, OPT_DECODER_MODE = 1, 2, 3, 4
 MODE_PARITY, MODE_NII, MODE_NII16 = 0, 1, 2
-KERNEL_AUTO, KERNEL_QUAD, KERNEL_TPF = 0, 1, 2
+KERNEL_AUTO, KERNEL_QUAD, KERNEL_TPF, KERNEL_LAT = 0, 1, 2, 3
 MOD_IDS = {'BPSK': 0, 'QPSK': 1, '8PSK': 2, '16QAM': 3, '64QAM': 4, '256QAM': 5}
 BPS = {'BPSK': 1, 'QPSK': 2, '8PSK': 3, '16QAM': 4, '64QAM': 6, '256QAM': 8}
 

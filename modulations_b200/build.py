@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200dvb.so")
-SOURCES = ["api.cu", "decode_quad.cu", "decode_tpf.cu", "decode_nii.cu", "encode.cu", "modem.cu", "waveform.cu", "microbench.cu"]
+SOURCES = ["api.cu", "decode_quad.cu", "decode_tpf.cu", "decode_nii.cu", "decode_lat.cu", "encode.cu", "modem.cu", "waveform.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=false",

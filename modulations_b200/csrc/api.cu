@@ -157,6 +157,8 @@ int b200dvb_codec_create(int N, const int32_t *next_state_h, const int32_t *out_
     if (rc != B200DVB_OK) { delete h; return rc; }
     rc = nii_configure(c);
     if (rc != B200DVB_OK) { delete h; return rc; }
+    rc = lat_configure(c);
+    if (rc != B200DVB_OK) { delete h; return rc; }
     // stream offsets (depuncture order of dvb_rcs2_turbo.py:476-487)
     c.h_tab = (int16_t *)malloc(sizeof(int16_t) * 7 * N);
     if (!c.h_tab) { delete h; return B200DVB_ENOMEM; }
@@ -239,6 +241,15 @@ int b200dvb_siso(b200dvb_codec_t codec, int B, const float *Lc_A, const float *L
 // 16-frame tile takes as long as a full wave (64 frames per SM); the quad kernel finishes a wave of 32 frames per
 // SM in 0.72x that time (profiles/r02_measure_pack1.txt: 0.75 ms against 1.05 ms at N=212), so batches that fit one
 // quad wave go there.  A pure function of (codec, B): the workspace query and the launch agree.
+// Batches of up to two frames per SM take the low-latency kernel (one CTA per frame: 0.26 ms per frame at N=212 against
+// 0.65 ms for a quad wave), whatever N.
+static bool use_lat(const Codec &c, int B)
+{
+    if (!c.lat_enabled) return false;
+    if (c.opt_kernel == 3) return true;
+    return c.opt_kernel == 0 && B <= c.lat_frames_per_wave;
+}
+
 static bool use_tpf(const Codec &c, int B)
 {
     if (!c.tpf.enabled || c.opt_kernel == 1) return false;
@@ -251,6 +262,7 @@ size_t b200dvb_decode_workspace_bytes(b200dvb_codec_t codec, int B)
 {
     if (!codec || B <= 0) return 0;
     if (codec->c.opt_mode != B200DVB_MODE_PARITY) return nii_workspace_bytes(codec->c, B);
+    if (use_lat(codec->c, B)) return 256;                            // the whole frame lives in shared memory
     return use_tpf(codec->c, B) ? tpf_workspace_bytes(codec->c, B) : decode_workspace_bytes(codec->c, B);
 }
 
@@ -260,8 +272,9 @@ int b200dvb_codec_set_option(b200dvb_codec_t codec, int option, int value)
     Codec &c = codec->c;
     switch (option) {
     case B200DVB_OPT_KERNEL:
-        if (value < 0 || value > 2) return B200DVB_EINVAL;
+        if (value < 0 || value > 3) return B200DVB_EINVAL;
         if (value == 2 && !c.tpf.enabled) return B200DVB_ENOSPEC;
+        if (value == 3 && !c.lat_enabled) return B200DVB_ENOSPEC;
         c.opt_kernel = value;
         return B200DVB_OK;
     case B200DVB_OPT_NO_ROW_STAGING: c.opt_no_row_staging = value != 0; return B200DVB_OK;
@@ -285,6 +298,8 @@ int b200dvb_decode(b200dvb_codec_t codec, int B, const float *llr, long long llr
     if (codec->c.opt_mode != B200DVB_MODE_PARITY)
         return nii_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
                                  workspace, workspace_bytes, (cudaStream_t)stream);
+    if (use_lat(codec->c, B))
+        return lat_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters, (cudaStream_t)stream);
     if (use_tpf(codec->c, B))
         return tpf_launch_decode(codec->c, B, llr, llr_stride, bits, packed, ref_bits, counters,
                                  workspace, workspace_bytes, (cudaStream_t)stream);

@@ -72,9 +72,10 @@ struct Codec {
     int num_sms = 0;
     int vec_ab = 0, vec_wy = 0;   // (A,B) / (W,Y) LLR pairs are adjacent and even-aligned in the stream
     // development / test switches (b200dvb_codec_set_option); all 0 in production
-    int opt_kernel = 0;           // 0: automatic choice per batch, 1: quad kernel, 2: thread-per-frame kernel
+    int opt_kernel = 0;           // 0: automatic choice per batch, 1: quad kernel, 2: thread-per-frame kernel, 3: low-latency kernel
     int opt_no_row_staging = 0;   // 1: thread-per-frame transposition without the cp.async row staging
     int opt_phase_timers = 0;     // 1: run the kernel instances that keep per-phase cycle counters
+    int lat_enabled = 0, lat_frames_per_wave = 0;   // low-latency kernel (decode_lat.cu): usable for this N; frames it takes at once
     int opt_mode = 0;             // decoder arithmetic: 0 = parity (the reference's), 1 = non-parity "nii" (B200DVB_MODE_NII)
     // device tables
     int16_t *d_tab = nullptr;     // [7][N] int16: perm, inv_perm, offA, offW1, offY1, offW2, offY2
@@ -113,6 +114,9 @@ int tpf_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
                       void *ws, size_t ws_bytes, cudaStream_t s);
 size_t tpf_workspace_bytes(const Codec &c, int B);
 int tpf_read_phase_cycles(double *out_h, int reset);
+int lat_configure(Codec &c);
+int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits, uint32_t *packed,
+                      const uint8_t *ref_bits, unsigned long long *counters, cudaStream_t s);
 int nii_configure(Codec &c);
 int nii_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits,
                       uint32_t *packed, const uint8_t *ref_bits, unsigned long long *counters,

@@ -1,0 +1,239 @@
+// decode_lat.cu — the LOW-LATENCY decode path: one CTA per frame, bit-exact with the reference
+// (dvb_rcs2_turbo.py:116-281 bcjr_max_log_map, :464-537 decode), for the reference's own call shape — one frame
+// per decode() (turbo_test_suite.py:138-164, test.py:56-92).
+//
+// Why a third kernel.  A frame is 16 SISOs of strictly sequential recursions: the throughput kernels amortise that
+// over 64 frames per SM, and a batch of ONE frame then costs what a full wave costs (thread-per-frame kernel: 0.99 ms
+// at N=212; quad kernel: 0.65 ms; profiles/r02_measure_pack1.txt).  Here everything that is NOT sequential is spread
+// over the 256 threads of a CTA, and the two recursions run as two lone threads with all 16 state metrics in
+// registers (tpf_core.cuh: 63 straight-line FP32 operations per step, no shuffle, no exchange):
+//   P0 (all threads, one trellis step each): a-priori gather, Y = Lc + La in float64, the merged branch-metric record;
+//   P1 (two threads): thread A runs alpha twice around the circular trellis and stores alpha[k] on the second lap,
+//       thread B does the same for beta (natural state labels), concurrently: 2 N sequential steps per SISO;
+//   P2 (all threads, one step each): the 64 a-posteriori sums of a step and the float64 extrinsic epilogue.
+// The whole frame lives in shared memory (240 bytes per couple: 51 KB at N=212, 204 KB at N=848), so the same kernel
+// serves every N of the reference's table.  It is a latency path, not a throughput path: api.cu dispatches batches
+// of up to a few hundred frames here, larger ones to the wave kernels.
+#include "common.cuh"
+#include "tpf_core.cuh"
+
+namespace b200dvb {
+
+namespace {
+
+using namespace tpf;
+
+constexpr int kLatThreads = 256;
+
+struct LatArgs {
+    int N, B, iterations, n_llr, num_sms;
+    double sf_inner, sf_last;
+    const int16_t *tab;             // [7][N]: perm, inv_perm, offA, offW1, offY1, offW2, offY2
+    const float *llr;
+    long long llr_stride;
+    int32_t *bits;
+    uint32_t *packed;
+    const uint8_t *ref_bits;
+    unsigned long long *counters;
+};
+
+__device__ __forceinline__ void ld16(const float *p, float (&v)[16])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = reinterpret_cast<const float4 *>(p)[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void st16(float *p, const float (&v)[16])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<float4 *>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void ld8(const float *p, float (&g)[8])
+{
+    const float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+}
+
+__global__ void __launch_bounds__(kLatThreads)
+lat_kernel(const LatArgs A)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int N = A.N, tid = threadIdx.x;
+    // shared-memory frame: [perm | inv] int16, then per couple: L1, L2 (float4), Le1, Le2, Y (double2), record (8 floats),
+    // alpha (16 floats), beta (16 floats; index k holds beta[k], k = 1 .. N)
+    int16_t *perm = reinterpret_cast<int16_t *>(sm);
+    int16_t *inv = perm + N;
+    unsigned char *p = sm + (((size_t)4 * N + 15) / 16) * 16;
+    float4 *L1 = reinterpret_cast<float4 *>(p); p += (size_t)N * 16;
+    float4 *L2 = reinterpret_cast<float4 *>(p); p += (size_t)N * 16;
+    double2 *Le1 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
+    double2 *Le2 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
+    double2 *Y = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
+    float *rec = reinterpret_cast<float *>(p); p += (size_t)N * 32;
+    float *Al = reinterpret_cast<float *>(p); p += (size_t)N * 64;
+    float *Be = reinterpret_cast<float *>(p); p += (size_t)(N + 1) * 64;
+    unsigned *words = reinterpret_cast<unsigned *>(p);              // packed hard decisions, ceil(2N/32) words
+    __shared__ int s_err[2];
+    // the two lone recursion threads sit in different warps (= different schedulers); a second CTA on the same SM
+    // uses the other two schedulers
+    const int wa = ((blockIdx.x / A.num_sms) & 1) ? 64 : 0, wb = wa + 32;
+
+    for (int frame = blockIdx.x; frame < A.B; frame += gridDim.x) {
+        __syncthreads();
+        const float *row = A.llr + (size_t)frame * A.llr_stride;
+        for (int i = tid; i < 2 * N; i += kLatThreads) perm[i] = A.tab[i];
+        if (tid < 2) s_err[tid] = 0;
+        for (int i = tid; i < (2 * N + 31) / 32; i += kLatThreads) words[i] = 0u;
+        __syncthreads();
+        // ---- de-puncture (:466-487) and gather the interleaved systematic pair (:507-512) ----
+        const int16_t *g_off = A.tab + 2 * N;
+        for (int k = tid; k < N; k += kLatThreads) {
+            const int oa = g_off[k], op = g_off[perm[k]];
+            const int o0 = g_off[N + k], o1 = g_off[2 * N + k], o2 = g_off[3 * N + k], o3 = g_off[4 * N + k];
+            L1[k] = make_float4(__ldg(row + oa), __ldg(row + oa + 1), o0 >= 0 ? __ldg(row + o0) : 0.f, o1 >= 0 ? __ldg(row + o1) : 0.f);
+            L2[k] = make_float4(__ldg(row + op), __ldg(row + op + 1), o2 >= 0 ? __ldg(row + o2) : 0.f, o3 >= 0 ? __ldg(row + o3) : 0.f);
+        }
+        __syncthreads();
+        for (int h = 0; h < 2 * A.iterations; ++h) {
+            const bool second = (h & 1) != 0, first = h == 0;
+            const double sf = (h >> 1) < A.iterations - 1 ? A.sf_inner : A.sf_last;
+            // ---- P0: a-priori gather, Y = Lc + La, branch-metric record (:131-160) ----
+            for (int k = tid; k < N; k += kLatThreads) {
+                const float4 x = second ? L2[k] : L1[k];
+                double2 la = make_double2(0.0, 0.0);
+                if (!first) la = second ? Le1[perm[k]] : Le2[inv[k]];
+                const double YA = d_add((double)x.x, la.x), YB = d_add((double)x.y, la.y);
+                float g[8];
+                make_record(YA, YB, x.z, x.w, g);
+                Y[k] = make_double2(YA, YB);
+                reinterpret_cast<float4 *>(rec + 8 * k)[0] = make_float4(g[0], g[1], g[2], g[3]);
+                reinterpret_cast<float4 *>(rec + 8 * k)[1] = make_float4(g[4], g[5], g[6], g[7]);
+            }
+            __syncthreads();
+            // ---- P1: the two recursions, twice around the circular trellis (:162-230) ----
+            if (tid == wa) {
+                float v[16], g[8], gn[8];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) v[s] = 0.f;
+                ld8(rec, g);
+                for (int k = 0; k < N; ++k) {                       // lap 1: from zeros
+                    ld8(rec + 8 * (k + 1 < N ? k + 1 : 0), gn);
+                    pass_step(v, g, false);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+                }
+                for (int k = 0; k < N; ++k) {                       // lap 2: alpha[0] <- alpha[N], stored
+                    ld8(rec + 8 * (k + 1 < N ? k + 1 : 0), gn);
+                    st16(Al + 16 * k, v);
+                    pass_step(v, g, false);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+                }
+            } else if (tid == wb) {
+                float z[16], g[8], gn[8];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) z[s] = 0.f;
+                ld8(rec + 8 * (N - 1), g);
+                for (int k = N - 1; k >= 0; --k) {                  // lap 1
+                    ld8(rec + 8 * (k > 0 ? k - 1 : N - 1), gn);
+                    bwd_step(z, g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+                }
+                for (int k = N - 1; k >= 0; --k) {                  // lap 2: beta[N] <- beta[0], stored
+                    ld8(rec + 8 * (k > 0 ? k - 1 : N - 1), gn);
+                    st16(Be + 16 * (k + 1), z);
+                    bwd_step(z, g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+                }
+            }
+            __syncthreads();
+            // ---- P2: a-posteriori maxima and the float64 extrinsic (:232-281) ----
+            double2 *LeOut = second ? Le2 : Le1;
+            for (int k = tid; k < N; k += kLatThreads) {
+                float x[16], zs[16], g[8], uv[4];
+                ld16(Al + 16 * k, x);
+                ld16(Be + 16 * (k + 1), zs);
+                ld8(rec + 8 * k, g);
+                ext_step(x, zs, g, uv);
+                const double2 y = Y[k];
+                double ea, eb;
+                make_extrinsic(uv, y.x, y.y, sf, ea, eb);
+                LeOut[k] = make_double2(ea, eb);
+            }
+            __syncthreads();
+        }
+        // ---- hard decision (:526-537) + optional error counting ----
+        int my_err = 0;
+        for (int k = tid; k < N; k += kLatThreads) {
+            const float4 ab = L1[k];
+            const double2 la = Le2[inv[k]], e1 = Le1[k];
+            const double LA = d_add(d_add((double)ab.x, la.x), e1.x);
+            const double LB = d_add(d_add((double)ab.y, la.y), e1.y);
+            const int bA = LA < 0.0, bB = LB < 0.0;
+            if (A.bits) *reinterpret_cast<int2 *>(A.bits + (size_t)frame * 2 * N + 2 * k) = make_int2(bA, bB);
+            atomicOr(&words[k >> 4], (unsigned)(bA | (bB << 1)) << (2 * (k & 15)));
+            if (A.ref_bits) {
+                const uint8_t *r = A.ref_bits + (size_t)frame * 2 * N + 2 * k;
+                my_err += (bA != r[0]) + (bB != r[1]);
+            }
+        }
+        if (my_err) atomicAdd(&s_err[0], my_err);
+        __syncthreads();
+        const int wpf = (2 * N + 31) / 32;
+        if (A.packed)
+            for (int i = tid; i < wpf; i += kLatThreads) A.packed[(size_t)frame * wpf + i] = words[i];
+        if (tid == 0 && A.counters) {
+            if (A.ref_bits) {
+                if (s_err[0]) { atomicAdd(A.counters + 0, (unsigned long long)s_err[0]); atomicAdd(A.counters + 1, 1ull); }
+            }
+            atomicAdd(A.counters + 2, 1ull);
+            atomicAdd(A.counters + 3, 2ull * N);
+        }
+    }
+}
+
+}  // namespace
+
+size_t lat_smem_bytes(int N)
+{
+    return (((size_t)4 * N + 15) / 16) * 16 + (size_t)N * (16 + 16 + 16 + 16 + 16 + 32 + 64) + (size_t)(N + 1) * 64 +
+           (size_t)((2 * N + 31) / 32) * 4 + 64;
+}
+
+int lat_configure(Codec &c)
+{
+    c.lat_enabled = 0;
+    int dev = 0;
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const size_t need = lat_smem_bytes(c.N);
+    if (need > (size_t)prop.sharedMemPerBlockOptin) return B200DVB_OK;
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    int occ = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel, kLatThreads, need));
+    if (occ < 1) return B200DVB_OK;
+    c.lat_enabled = 1;
+    c.lat_frames_per_wave = (occ < 2 ? occ : 2) * prop.multiProcessorCount;   // at most two CTAs per SM: one lone thread per scheduler
+    return B200DVB_OK;
+}
+
+int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_stride, int32_t *bits, uint32_t *packed,
+                      const uint8_t *ref_bits, unsigned long long *counters, cudaStream_t s)
+{
+    if (B == 0) return B200DVB_OK;
+    LatArgs A{};
+    A.N = c.N; A.B = B; A.iterations = c.iterations; A.n_llr = c.n_llr; A.num_sms = c.num_sms;
+    A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
+    A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed; A.ref_bits = ref_bits; A.counters = counters;
+    const int grid = B < c.lat_frames_per_wave ? B : c.lat_frames_per_wave;
+    lat_kernel<<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
+    B2_CUDA(cudaGetLastError());
+    return B200DVB_OK;
+}
+
+}  // namespace b200dvb

@@ -161,7 +161,7 @@ class _CodecHandle:
         self._ws = {}
         if kernel is not None:
             self.set_option(_lib.OPT_KERNEL, {"auto": _lib.KERNEL_AUTO, "quad": _lib.KERNEL_QUAD,
-                                              "tpf": _lib.KERNEL_TPF}[kernel])
+                                              "tpf": _lib.KERNEL_TPF, "lat": _lib.KERNEL_LAT}[kernel])
         if mode is not None:
             self.set_option(_lib.OPT_DECODER_MODE, mode)
         self.frames_per_wave = int(lib.b200dvb_codec_frames_per_wave(h))    # depends on the decoder mode
@@ -362,7 +362,7 @@ class DVBRCS2_Turbo:
         replacing the committed one, whose formula is not a permutation (BER ~ 0.2 at every
         SNR).  With a bijective ``perm`` the same kernels decode properly; results are then compared with
         the oracle given the same table, and reported as a labelled non-parity run.
-        ``kernel`` (development / tests): "auto" (default), "quad" or "tpf" forces one decode kernel.
+        ``kernel`` (development / tests): "auto" (default), "quad", "tpf" or "lat" forces one decode kernel.
         ``boundary`` (extension): "double-pass" (default) is the reference's decoder, bit-exact
         (dvb_rcs2_turbo.py:162-230: every recursion runs twice around the circular trellis).  "nii" is a
         NON-PARITY mode: one pass per SISO, alpha[0] / beta[N] initialised from the metrics the same constituent

@@ -151,3 +151,30 @@ def test_noise_variance_estimate(name):
         want = max(float(np.mean(np.abs(rx[:len(const)] - const) ** 2)), 0.02)
         got = estimate_noise_var(rx, name)
         assert abs(got - want) <= 1e-12 + 1e-9 * want, (name, sigma, got, want)
+
+
+@pytest.mark.parametrize("N,rate,iters", [(48, '1/3', 8), (48, '3/4', 3), (64, '2/3', 2), (212, '1/3', 8), (212, '1/2', 8),
+                                          (220, '1/3', 2), (424, '1/2', 2), (752, '1/2', 8), (848, '1/3', 2)])
+def test_low_latency_kernel(N, rate, iters):
+    """decode_lat.cu (one CTA per frame, the whole frame in shared memory): every N of the reference's table, int32 /
+    packed output, counters, more frames than one pass of the grid — bit-exact against the oracle — and the one-frame
+    `decode()` call of the reference goes through it."""
+    import torch
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    g = turbo.DVBRCS2_Turbo(N, rate, iters, kernel="lat")
+    o = oracle.OracleTurbo(N, rate, iters, perm=g.perm, inv_perm=g.inv_perm)
+    B = 330 if N <= 220 else 40
+    info, llr = _mc(g, ((B + 15) // 16) * 16, 2.0, 31 + N)
+    info, llr = info[:B], llr[:B].contiguous()
+    x = llr.cpu().numpy()
+    ref = o.decode_batch(x, threads=os.cpu_count() or 1)
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    dec = g.decode_batch(llr, ref_bits=info, counters=cnt)
+    assert np.array_equal(dec.cpu().numpy(), ref)
+    i = info.cpu().numpy()
+    c = cnt.cpu().numpy()
+    assert c[0] == np.sum(ref != i) and c[1] == np.sum(np.any(ref != i, axis=1)) and c[2] == B and c[3] == B * 2 * N
+    assert np.array_equal(turbo.unpack_bits(g.decode_batch(llr, out="packed").cpu(), 2 * N), ref)
+    auto = turbo.DVBRCS2_Turbo(N, rate, iters)                      # production dispatch: one frame -> this kernel
+    assert np.array_equal(auto.decode(x[0]), ref[0])
+    assert np.array_equal(auto.decode_batch(x[:3]), ref[:3])

@@ -32,7 +32,7 @@ def test_kernels_agree_on_tile_boundaries(N, rate, iters, nfr):
     o = oracle.OracleTurbo(N, rate, iters)
     info, llr = _llrs(o, N, rate, nfr, 2.0, 99 + N + nfr)
     ref = o.decode_batch(llr)
-    for kernel in ("tpf", "quad", "auto"):
+    for kernel in ("tpf", "quad", "lat", "auto"):
         g = _codec(N, rate, iters, kernel)
         dec = g.decode_batch(llr)
         assert np.array_equal(dec, ref), f"{kernel} kernel, N={N} R={rate} B={nfr}: {np.sum(dec != ref)} bits differ"

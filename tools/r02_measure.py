@@ -44,9 +44,10 @@ def turbo_rate(c):
 
 if "lat" in which:
     print("# decode latency vs batch, N=212 R=1/3 8 it: resident (device tensors, CUDA events) and decode()/decode_batch on numpy (wall)")
-    for kern in ("tpf", "quad", "auto"):
+    for kern in ("tpf", "quad", "lat", "auto"):
         c = turbo.DVBRCS2_Turbo(212, '1/3', 8, kernel=kern)
-        for B in (1, 16, 256, 4096, 65536):
+        for B in (1, 16, 148, 296, 1024, 4096, 65536):
+            if kern == "lat" and B > 4096: continue
             info, llr = gen(c, max(B, 16))
             llr = llr[:B].contiguous()
             best, med = timeit(lambda: c.decode_batch(llr, out="packed"))

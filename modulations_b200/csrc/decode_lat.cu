@@ -5,11 +5,16 @@
 // Why a third kernel.  A frame is 16 SISOs of strictly sequential recursions: the throughput kernels amortise that
 // over 64 frames per SM, and a batch of ONE frame then costs what a full wave costs (thread-per-frame kernel: 0.99 ms
 // at N=212; quad kernel: 0.65 ms; profiles/r02_measure_pack1.txt).  Here everything that is NOT sequential is spread
-// over the 256 threads of a CTA, and the two recursions run as two lone threads with all 16 state metrics in
-// registers (tpf_core.cuh: 63 straight-line FP32 operations per step, no shuffle, no exchange):
+// over the 256 threads of a CTA, and the two recursions run as two lone warps, one state metric per lane (4 shuffles +
+// 7 FP32 operations per step: 77 cycles, against 120 for one thread holding all 16 states, whose 63 operations are
+// issue-bound), and the second lap of a recursion stops as soon as it has provably re-joined the first:
 //   P0 (all threads, one trellis step each): a-priori gather, Y = Lc + La in float64, the merged branch-metric record;
-//   P1 (two threads): thread A runs alpha twice around the circular trellis and stores alpha[k] on the second lap,
-//       thread B does the same for beta (natural state labels), concurrently: 2 N sequential steps per SISO;
+//   P1 (two warps): warp A runs alpha around the circular trellis, storing alpha[k]; the second lap (:182-183: it
+//       starts from the first lap's end state) overwrites them and STOPS where its 16 metrics equal, bit for bit,
+//       what the first lap stored at that position: from there on it would reproduce the first lap (deterministic
+//       recursion, same inputs), whose values are already in place.  Exact; on noisy N=212 codewords the laps
+//       re-join after 40 steps on average (p99: 108, measured with the oracle), so a SISO is ~N + 50 sequential
+//       steps instead of 2 N.  Warp B does the same for beta (natural state labels), concurrently;
 //   P2 (all threads, one step each): the 64 a-posteriori sums of a step and the float64 extrinsic epilogue.
 // The whole frame lives in shared memory (240 bytes per couple: 51 KB at N=212, 204 KB at N=848), so the same kernel
 // serves every N of the reference's table.  It is a latency path, not a throughput path: api.cu dispatches batches
@@ -55,6 +60,7 @@ __device__ __forceinline__ void ld8(const float *p, float (&g)[8])
     const float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
     g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
 }
+
 
 __global__ void __launch_bounds__(kLatThreads)
 lat_kernel(const LatArgs A)
@@ -113,41 +119,67 @@ lat_kernel(const LatArgs A)
             }
             __syncthreads();
             // ---- P1: the two recursions, twice around the circular trellis (:162-230) ----
-            if (tid == wa) {
-                float v[16], g[8], gn[8];
-#pragma unroll
-                for (int s = 0; s < 16; ++s) v[s] = 0.f;
-                ld8(rec, g);
-                for (int k = 0; k < N; ++k) {                       // lap 1: from zeros
-                    ld8(rec + 8 * (k + 1 < N ? k + 1 : 0), gn);
-                    pass_step(v, g, false);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+            // One state per lane (16 lanes of a warp, the upper half-warp mirrors the lower): the new metric of a state
+            // needs two old ones and the normaliser n[0] two more, so a step is 4 shuffles -> 2 x (add, add, max) ->
+            // subtract: a chain of dependent latencies instead of the ~120 issue cycles one thread needs for all 16
+            // states.  Same operations on the same operands as tpf::pass_step / tpf::bwd_step, so the bits agree.
+            // The second lap stops where it has re-joined the first: the recursion is deterministic, so once the 16
+            // metrics of lap 2 equal, bit for bit, what lap 1 left at the same trellis position, every later position
+            // of lap 2 would reproduce lap 1's values, which are already in place.  Measured with the oracle on
+            // N=212 noisy codewords: re-joined after 40 steps on average (p99 108); a lap that never re-joins runs
+            // to the end as before.  Exact, not an approximation: the exit is taken on verified equality only.
+            // Measured (profiles/r02_latency.txt): 77 cycles per step, of which 59 are the bare dependent chain (shuffle
+            // ~36 + add + max + subtract; timing-only builds without the bookkeeping).  Exchanging the metrics through
+            // the shared-memory cell they are stored in anyway was 10 % slower than the shuffles, and hand-ordered
+            // schedules (shuffles first; bookkeeping in the shadow of the arithmetic; loads made dependent on an add)
+            // all lost 3-14 % to the compiler's: a load issued after the shuffles holds the adds back.
+            if ((tid >> 5) == (wa >> 5)) {
+                const int s = tid & 15, t = s >> 1, c2 = 2 * cls(t);
+                const bool swp = (((t >> 2) ^ s) & 1) != 0;         // X (for v[t]) is the odd entry of the class pair
+                const float2 *rp = reinterpret_cast<const float2 *>(rec) + (c2 >> 1);
+                const float2 *r0 = reinterpret_cast<const float2 *>(rec);
+                float v = 0.f;
+                float2 pc = rp[0], p0 = r0[0];
+                for (int lap = 0; lap < 2; ++lap) {
+                    bool joined = false;
+                    for (int k = 0; k < N; ++k) {
+                        if (joined) break;                          // (tested one step late: the vote stays off the chain)
+                        const int kn = k + 1 < N ? k + 1 : 0;
+                        const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
+                        if (lap) joined = __all_sync(0xffffffffu, __float_as_uint(Al[16 * k + s]) == __float_as_uint(v));
+                        if ((tid & 16) == 0) Al[16 * k + s] = v;
+                        const float a = __shfl_sync(0xffffffffu, v, t, 16), bq = __shfl_sync(0xffffffffu, v, 8 + t, 16);
+                        const float v0 = __shfl_sync(0xffffffffu, v, 0, 16), v8 = __shfl_sync(0xffffffffu, v, 8, 16);
+                        const float X = swp ? pc.y : pc.x, Yv = swp ? pc.x : pc.y;
+                        const float n = f_max(f_add(a, X), f_add(bq, Yv));
+                        const float n0 = f_max(f_add(v0, p0.x), f_add(v8, p0.y));
+                        v = f_sub(n, n0);
+                        pc = pn; p0 = p0n;
+                    }
                 }
-                for (int k = 0; k < N; ++k) {                       // lap 2: alpha[0] <- alpha[N], stored
-                    ld8(rec + 8 * (k + 1 < N ? k + 1 : 0), gn);
-                    st16(Al + 16 * k, v);
-                    pass_step(v, g, false);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
-                }
-            } else if (tid == wb) {
-                float z[16], g[8], gn[8];
-#pragma unroll
-                for (int s = 0; s < 16; ++s) z[s] = 0.f;
-                ld8(rec + 8 * (N - 1), g);
-                for (int k = N - 1; k >= 0; --k) {                  // lap 1
-                    ld8(rec + 8 * (k > 0 ? k - 1 : N - 1), gn);
-                    bwd_step(z, g);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
-                }
-                for (int k = N - 1; k >= 0; --k) {                  // lap 2: beta[N] <- beta[0], stored
-                    ld8(rec + 8 * (k > 0 ? k - 1 : N - 1), gn);
-                    st16(Be + 16 * (k + 1), z);
-                    bwd_step(z, g);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g[i] = gn[i];
+            } else if ((tid >> 5) == (wb >> 5)) {
+                const int s = tid & 15, t = s & 7, c2 = 2 * cls(t);
+                const bool swp = (((t >> 2) ^ (s >> 3)) & 1) != 0;
+                const float2 *rp = reinterpret_cast<const float2 *>(rec) + (c2 >> 1);
+                const float2 *r0 = reinterpret_cast<const float2 *>(rec);
+                float z = 0.f;
+                float2 pc = rp[4 * (N - 1)], p0 = r0[4 * (N - 1)];
+                for (int lap = 0; lap < 2; ++lap) {
+                    bool joined = false;
+                    for (int k = N - 1; k >= 0; --k) {
+                        if (joined) break;
+                        const int kn = k > 0 ? k - 1 : N - 1;
+                        const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
+                        if (lap) joined = __all_sync(0xffffffffu, __float_as_uint(Be[16 * (k + 1) + s]) == __float_as_uint(z));
+                        if ((tid & 16) == 0) Be[16 * (k + 1) + s] = z;
+                        const float a = __shfl_sync(0xffffffffu, z, 2 * t, 16), bq = __shfl_sync(0xffffffffu, z, 2 * t + 1, 16);
+                        const float z0 = __shfl_sync(0xffffffffu, z, 0, 16), z1 = __shfl_sync(0xffffffffu, z, 1, 16);
+                        const float X = swp ? pc.y : pc.x, Yv = swp ? pc.x : pc.y;
+                        const float n = f_max(f_add(a, X), f_add(bq, Yv));
+                        const float n0 = f_max(f_add(z0, p0.x), f_add(z1, p0.y));
+                        z = f_sub(n, n0);
+                        pc = pn; p0 = p0n;
+                    }
                 }
             }
             __syncthreads();
@@ -212,8 +244,11 @@ int lat_configure(Codec &c)
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
     const size_t need = lat_smem_bytes(c.N);
-    if (need > (size_t)prop.sharedMemPerBlockOptin) return B200DVB_OK;
-    B2_CUDA(cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    cudaFuncAttributes fa;
+    B2_CUDA(cudaFuncGetAttributes(&fa, lat_kernel));
+    const size_t cap = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;   // the static words count against the limit
+    if (need > cap) return B200DVB_OK;
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     int occ = 0;
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel, kLatThreads, need));
     if (occ < 1) return B200DVB_OK;

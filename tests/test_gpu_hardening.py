@@ -23,14 +23,15 @@ def _mc(g, B, ebn0_db, seed):
 
 
 @pytest.mark.parametrize("kernel,N,rate,B", [("tpf", 212, '1/3', 100_000), ("quad", 212, '1/3', 20_000),
-                                             ("tpf", 48, '1/2', 100_000), ("quad", 424, '1/3', 6_000)])
+                                             ("tpf", 48, '1/2', 100_000), ("quad", 424, '1/3', 6_000),
+                                             ("lat", 212, '1/3', 20_000), ("lat", 752, '1/2', 3_000)])
 def test_randomised_large_batch_vs_oracle(kernel, N, rate, B):
     """10^5 DISTINCT frames (device Philox source, Eb/N0 2 dB) through the CUDA decoder and through the C oracle
     on every host thread: every hard decision must agree.  Distinct inputs in every tile and wave are what a
     stale-scratch / discarded-L2-line race would corrupt; repeated fixtures cannot show that."""
     from modulations_b200 import dvb_rcs2_turbo as turbo
     iters = 8 if N <= 212 else 4
-    g = turbo.DVBRCS2_Turbo(N, rate, iters, kernel=kernel if N <= 212 else "quad")
+    g = turbo.DVBRCS2_Turbo(N, rate, iters, kernel=kernel if (N <= 212 or kernel == "lat") else "quad")
     o = oracle.OracleTurbo(N, rate, iters, perm=g.perm, inv_perm=g.inv_perm)
     info, llr = _mc(g, B, 2.0, 2026 + N)
     packed = g.decode_batch(llr, out="packed")
@@ -178,3 +179,26 @@ def test_low_latency_kernel(N, rate, iters):
     auto = turbo.DVBRCS2_Turbo(N, rate, iters)                      # production dispatch: one frame -> this kernel
     assert np.array_equal(auto.decode(x[0]), ref[0])
     assert np.array_equal(auto.decode_batch(x[:3]), ref[:3])
+
+
+@pytest.mark.parametrize("N,rate", [(48, '1/3'), (212, '1/3'), (212, '3/4'), (424, '1/2')])
+def test_low_latency_kernel_lap_rejoin_edge_cases(N, rate):
+    """The low-latency kernel ends the second lap of a recursion where it has re-joined the first (decode_lat.cu).
+    Inputs at both ends of that test: all-zero and constant LLRs (re-joined at once), pure-noise LLRs (on short frames
+    most recursions never re-join: the full second lap runs), saturated +-50 LLRs (the reference's clip level), and a
+    frame of +-0.0 — all bit-exact against the oracle."""
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    g = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="lat")
+    o = oracle.OracleTurbo(N, rate, 8, perm=g.perm, inv_perm=g.inv_perm)
+    rng = np.random.RandomState(N)
+    n = g.n_llr
+    x = np.zeros((24, n), dtype=np.float32)
+    x[1] = 1.25
+    x[2] = -50.0
+    x[3] = np.where(rng.rand(n) < 0.5, -50.0, 50.0)
+    x[4] = np.where(rng.rand(n) < 0.5, -0.0, 0.0)
+    x[5:16] = rng.randn(11, n) * 3.0
+    x[16:20] = rng.randn(4, n) * 0.01
+    x[20:24] = np.clip(rng.randn(4, n) * 40.0, -50, 50)
+    ref = o.decode_batch(x, threads=os.cpu_count() or 1)
+    assert np.array_equal(g.decode_batch(x), ref)

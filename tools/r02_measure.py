@@ -58,6 +58,19 @@ if "lat" in which:
                 t0 = time.perf_counter(); c.decode_batch(xh); t.append(time.perf_counter() - t0)
             print(f"{kern:5s} B={B:6d}: resident {best*1e3:9.1f} us (median {med*1e3:9.1f})  = {B/best/1e3:8.3f} Mframes/s | numpy in/out wall {min(t)*1e6:9.1f} us")
 
+if "latvar" in which:
+    print("# low-latency kernel, one frame resident, 8 it")
+    for N, rate in ((48, '1/3'), (212, '1/3'), (752, '1/2')):
+        ref = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="quad")
+        c = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="lat")
+        info, llr = gen(c, 16)
+        want = ref.decode_batch(llr)
+        for var in (0,):
+            ok = bool(torch.equal(c.decode_batch(llr), want))
+            one = llr[:1].contiguous()
+            best, med = timeit(lambda: c.decode_batch(one, out="packed"))
+            print(f"N={N:4d} R={rate} variant {var}: {best*1e3:8.1f} us (median {med*1e3:8.1f})  bit-exact vs quad: {ok}")
+
 if "long" in which:
     print("# long frames (table N), 8 it, resident, B sized to ~4 waves; % of the 64 ACS/clk/SM roofline at 1965 MHz")
     for N, rate in ((48, '1/3'), (64, '1/3'), (212, '1/3'), (212, '1/2'), (220, '1/3'), (424, '1/3'), (752, '1/2'), (752, '1/3'), (848, '1/3')):

@@ -211,6 +211,7 @@ int b200dvb_codec_frames_per_wave(b200dvb_codec_t codec)
     const Codec &c = codec->c;
     if (c.opt_mode == B200DVB_MODE_NII16) return c.num_sms * kTpfWarps * kTpfFrames * 2;   // two frames per lane
     if (c.opt_mode == B200DVB_MODE_NII || c.tpf.enabled) return c.num_sms * kTpfWarps * kTpfFrames;
+    if (c.geom_g.frames > 0) return c.num_sms * c.geom_g.ctas_per_sm * c.geom_g.frames;   // long frames, large batches
     return c.num_sms * c.geom.ctas_per_sm * c.geom.frames;
 }
 

@@ -42,6 +42,7 @@ struct QuadGeom {
     int y_slots;      // > 0: Y = Lc + La is parked in TMEM, this many positions per thread
     int frames;       // frames per CTA (8 * groups, or 4/2/1 when even one group does not fit)
     int ctas_per_sm;
+    int grec;         // branch-metric records live in the (L1/L2-cached) global workspace, not in shared memory
     size_t smem_bytes;
 };
 
@@ -67,6 +68,7 @@ struct Codec {
     int N = 0, period = 0, iterations = 0, n_llr = 0;
     double sf_inner = 0.7, sf_last = 1.0;
     QuadGeom geom{};
+    QuadGeom geom_g{};            // long frames: the same kernel with its records in global memory (geom_g.grec = 1) or frames = 0
     TpfGeom tpf{};
     TpfGeom nii{};                // geometry of the non-parity "nii" mode (decode_nii.cu)
     int num_sms = 0;

@@ -54,6 +54,7 @@ struct QuadArgs {
     int timed;            // development: add this launch's per-phase cycles to g_phase_cycles
     // workspace
     double2 *Le1, *Le2, *Y;
+    float *grec;          // geometry `grec`: [CTA][frame slot][rec_stride] branch-metric records
 };
 
 // phase timers (SM cycles summed over CTAs): 0 prep, 1 recursion in (pass 1 + pass 2 to the
@@ -68,6 +69,20 @@ __device__ __forceinline__ void split_pos(int i, int N, unsigned magic, int &f, 
 {
     f = (int)__umulhi((unsigned)i, magic);
     k = i - f * N;
+}
+
+// The same for the global-record geometry: a warp takes 8 frames x 4 consecutive steps, so that its record stores (and
+// the reads of the extrinsic maxima) cover 4 x 256 contiguous bytes of the [group][step][8 frames] layout, and its LLR /
+// Y / extrinsic accesses 32 or 64 contiguous bytes per frame (N is a multiple of 4).
+template <bool GREC>
+__device__ __forceinline__ void pos_of(int i, int N, unsigned magic, int &f, int &k)
+{
+    split_pos(i, N, magic, f, k);
+    if (GREC) {
+        const int idx = (f & 7) * N + k;
+        k = 4 * (idx >> 5) + (idx & 3);
+        f = (f & ~7) + ((idx >> 2) & 7);
+    }
 }
 
 __device__ __forceinline__ int cls2(int s)
@@ -95,24 +110,25 @@ __device__ __forceinline__ int xbase(int q) { return 16 * q + 4 * (q >> 1); }
 struct G2 { float2 a0, b0, a1, b1; };
 struct GH { float2 gA, gB, hA, hB; };
 
+template <int SS>       // SS: floats between the records of consecutive steps (8: frame-major; 64: 8 frames interleaved)
 struct Recs {           // per-lane pointers into this frame's records
     const float *pA0, *pB0, *pA1, *pB1;     // (g0,g1) of butterfly A/B in record k (even) / k+1
     int dA0, dB0, dA1, dB1;                 // float distance from the g pair to the h pair (class ~c)
     __device__ __forceinline__ G2 pair(int k_even) const {
         G2 g;
-        g.a0 = *reinterpret_cast<const float2 *>(pA0 + k_even * 8);
-        g.b0 = *reinterpret_cast<const float2 *>(pB0 + k_even * 8);
-        g.a1 = *reinterpret_cast<const float2 *>(pA1 + k_even * 8);
-        g.b1 = *reinterpret_cast<const float2 *>(pB1 + k_even * 8);
+        g.a0 = *reinterpret_cast<const float2 *>(pA0 + k_even * SS);
+        g.b0 = *reinterpret_cast<const float2 *>(pB0 + k_even * SS);
+        g.a1 = *reinterpret_cast<const float2 *>(pA1 + k_even * SS);
+        g.b1 = *reinterpret_cast<const float2 *>(pB1 + k_even * SS);
         return g;
     }
     template <int KPAR> __device__ __forceinline__ void one(int k, float2 &gA, float2 &gB) const {
-        const int e = (k - KPAR) * 8;
+        const int e = (k - KPAR) * SS;
         gA = *reinterpret_cast<const float2 *>((KPAR ? pA1 : pA0) + e);
         gB = *reinterpret_cast<const float2 *>((KPAR ? pB1 : pB0) + e);
     }
     template <int KPAR> __device__ __forceinline__ GH ext(int k) const {
-        const int e = (k - KPAR) * 8;
+        const int e = (k - KPAR) * SS;
         const float *a = (KPAR ? pA1 : pA0) + e, *b = (KPAR ? pB1 : pB0) + e;
         GH g;
         g.gA = *reinterpret_cast<const float2 *>(a);
@@ -267,8 +283,8 @@ __device__ __forceinline__ void ext_step(float (&a)[4], float (&b)[4], const GH 
 // Branch metrics are always loaded one step (or one step pair) ahead of their use:
 // the exchange-buffer stores in between would otherwise pin the loads behind them.
 // ---------------------------------------------------------------------------
-template <int LEN, class CK>
-__device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const Recs &R,
+template <int LEN, int SS, class CK>
+__device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const Recs<SS> &R,
                                              const CK &ck, int ck_idx, int j0, const Lane &L, Xch &x)
 {
     float wb[LEN][4];
@@ -289,7 +305,7 @@ __device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const R
     GH G = R.template ext<0>(j0), Gn = G;
 #pragma unroll
     for (int i = 0; i < LEN; ++i) {
-        float *rec = grec + (j0 + i) * 8;
+        float *rec = grec + (j0 + i) * SS;
         if (i + 1 < LEN) {
             if ((i + 1) & 1) Gn = R.template ext<1>(j0 + i + 1); else Gn = R.template ext<0>(j0 + i + 1);
         }
@@ -303,8 +319,8 @@ __device__ __forceinline__ void window_alpha(float (&r)[4], float *grec, const R
     }
 }
 
-template <class CK>
-__device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Recs &R,
+template <int SS, class CK>
+__device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Recs<SS> &R,
                                             const CK &ck, int ck_idx, int j0, const Lane &L, Xch &x)
 {
     float wa[kWin][4];
@@ -325,7 +341,7 @@ __device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Re
     GH G = R.template ext<1>(j0 + kWin - 1), Gn = G;
 #pragma unroll
     for (int i = kWin - 1; i >= 0; --i) {
-        float *rec = grec + (j0 + i) * 8;
+        float *rec = grec + (j0 + i) * SS;
         if (i > 0) {
             if ((i - 1) & 1) Gn = R.template ext<1>(j0 + i - 1); else Gn = R.template ext<0>(j0 + i - 1);
         }
@@ -339,25 +355,88 @@ __device__ __forceinline__ void window_beta(float (&r)[4], float *grec, const Re
     }
 }
 
-template <class CK>
-__device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const CK &ck, float *xch,
+// Records in global memory (GREC, long frames): [group][step][8 frames][8 floats], so that the records of one step of
+// a warp's 8 frames are 256 contiguous bytes.  The recursion warps do not read them from global memory (through L1
+// every first touch of a sector was a miss whatever prefetch.global.L1 was issued ahead: measured, 51 % L1 hit rate,
+// long-scoreboard stalls 37 %) but from a private shared-memory ring that cp.async keeps kFeedAhead step pairs ahead:
+// one 16-byte LDGSTS per lane and step pair.  The loops read "their" pair at its ring position, the frame-major code
+// path reads it at its step index: the same Recs arithmetic serves both.
+constexpr int kGrecStep = 64;        // floats between the records of consecutive steps
+constexpr int kRingSteps = 32;       // ring capacity in steps (8 KB per recursion warp)
+constexpr int kFeedAhead = 8;        // step pairs in flight ahead of the one being read (kFeedAhead + 2 <= kRingSteps / 2)
+
+__device__ __forceinline__ void q_cpa16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void q_cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void q_cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+// Step pairs of the "in" phase in the order the warp consumes them: alpha 0, 2, .. N-2 (pass 1), 0, 2, .. M (pass 2 and
+// its last look-ahead); beta N-2, N-4, .. 0 (pass 1), N-2, .. (pass 2).
+struct Feed {
+    float *ring;              // this warp's ring
+    const float *src;         // this group's records in global memory
+    int N, lane, beta, total, iss, rd;
+    __device__ __forceinline__ int pair_k(int i) const {
+        const int h = N >> 1;
+        const int j = i < h ? i : i - h;
+        return beta ? N - 2 - 2 * j : 2 * j;
+    }
+    __device__ __forceinline__ void issue() {
+        if (iss < total) {
+            int k = pair_k(iss);
+            k = k < 0 ? 0 : k;
+            const int st = ((iss * 2) & (kRingSteps - 1)) + (lane >> 4);
+            q_cpa16(ring + st * kGrecStep + (lane & 15) * 4, src + (size_t)(k + (lane >> 4)) * kGrecStep + (lane & 15) * 4);
+        }
+        q_cpa_commit();       // (an empty group keeps the wait arithmetic uniform)
+        ++iss;
+    }
+    __device__ __forceinline__ void start() {
+        iss = rd = 0;
+        for (int i = 0; i <= kFeedAhead; ++i) issue();
+    }
+    // ring step index of the next pair to read; its data is complete when this returns
+    __device__ __forceinline__ int next_slot() {
+        issue();
+        q_cpa_wait<kFeedAhead + 1>();
+        __syncwarp();
+        const int st = (rd * 2) & (kRingSteps - 1);
+        ++rd;
+        return st;
+    }
+};
+
+template <bool PF, class CK>
+__device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const CK &ck, float *xch, float *rings,
                                           int warp, int xslot, const Lane &L, long long &t_mid)
 {
     const int N = g.N, M = g.M;
-    float *grec = gam + L.q * g.rec_stride;
+    constexpr int SS = PF ? kGrecStep : 8;
+    float *ggrp = gam + (size_t)(L.q >> 3) * N * kGrecStep;                  // (GREC) this group's records
+    float *grec = PF ? ggrp + (L.q & 7) * 8 : gam + L.q * g.rec_stride;     // this frame's records (written by ext_step)
+    float *ring = rings + xslot * (kRingSteps * kGrecStep);
+    float *rbase = PF ? ring + (L.q & 7) * 8 : grec;                        // what the recursion reads
     Xch x{xch + xslot * 2 * kXchFloats, xch + xslot * 2 * kXchFloats + kXchFloats};
-    Recs R;
-    R.pA0 = grec + L.oA[0];     R.pB0 = grec + L.oB[0];
-    R.pA1 = grec + 8 + L.oA[1]; R.pB1 = grec + 8 + L.oB[1];
+    Recs<SS> R;
+    R.pA0 = rbase + L.oA[0];      R.pB0 = rbase + L.oB[0];
+    R.pA1 = rbase + SS + L.oA[1]; R.pB1 = rbase + SS + L.oB[1];
     R.dA0 = 6 - 2 * L.oA[0]; R.dB0 = 6 - 2 * L.oB[0];
     R.dA1 = 6 - 2 * L.oA[1]; R.dB1 = 6 - 2 * L.oB[1];
+    Feed F;
+    F.ring = ring; F.src = ggrp; F.N = N; F.lane = threadIdx.x & 31; F.beta = warp;
+    F.total = warp ? (N >> 1) + ((N - M) >> 1) + 1 : (N >> 1) + (M >> 1) + 1;
+    if (PF) F.start();
+    // the pair at step k (frame-major records) or the next pair of the feed (ring)
+    auto pair_at = [&](int k) -> G2 { return PF ? R.pair(F.next_slot()) : R.pair(k); };
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (warp == 0) {
         // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183)
-        G2 cur = R.pair(0);
+        G2 cur = pair_at(0);
 #pragma unroll 2
         for (int k = 0; k < N; k += 2) {
-            const G2 nxt = R.pair(k + 2 < N ? k + 2 : 0);
+            const G2 nxt = pair_at(k + 2 < N ? k + 2 : 0);
             stepg(r, cur.a0, cur.b0);
             stepg(r, cur.a1, cur.b1);
             transpose_fwd(r, x.next(), L);
@@ -368,7 +447,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
             ck.store(k / kWin, r);
 #pragma unroll
             for (int j = 0; j < kWin; j += 2) {
-                const G2 nxt = R.pair(k + j + 2);          // k + j + 2 <= M < N
+                const G2 nxt = pair_at(k + j + 2);         // k + j + 2 <= M < N
                 stepg(r, cur.a0, cur.b0);
                 stepg(r, cur.a1, cur.b1);
                 transpose_fwd(r, x.next(), L);
@@ -377,10 +456,10 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
         }
     } else {
         // beta pass 1 (:203-213): j = N..2, then beta[N] <- beta[0] (:216-217)
-        G2 cur = R.pair(N - 2);
+        G2 cur = pair_at(N - 2);
 #pragma unroll 2
         for (int j = N; j > 0; j -= 2) {
-            const G2 nxt = R.pair(j >= 4 ? j - 4 : N - 2);
+            const G2 nxt = pair_at(j >= 4 ? j - 4 : N - 2);
             stepg(r, cur.a1, cur.b1);      // gamma[j-1] (odd)
             stepg(r, cur.a0, cur.b0);      // gamma[j-2] (even)
             transpose_bwd(r, x.next(), L);
@@ -392,7 +471,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
         if (ragged) {
             ck.store(g.nckA + g.nckB - 1, r);
             for (int t = 0; t < ragged; t += 2, j -= 2) {
-                const G2 nxt = R.pair(j - 4);
+                const G2 nxt = pair_at(j - 4);
                 stepg(r, cur.a1, cur.b1);
                 stepg(r, cur.a0, cur.b0);
                 transpose_bwd(r, x.next(), L);
@@ -403,7 +482,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
             ck.store(g.nckA + (j - M) / kWin - 1, r);
 #pragma unroll
             for (int t = 0; t < kWin; t += 2) {
-                const G2 nxt = R.pair(j - t - 4);           // >= M - 4 >= 4
+                const G2 nxt = pair_at(j - t - 4);          // >= M - 4 >= 4
                 stepg(r, cur.a1, cur.b1);
                 stepg(r, cur.a0, cur.b0);
                 transpose_bwd(r, x.next(), L);
@@ -411,20 +490,67 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
             }
         }
     }
+    if (PF) { q_cpa_wait<0>(); __syncwarp(); }
     ck.publish();
     __syncthreads();
     ck.acquire();
     t_mid = clock64();
+    // "out" phase.  GREC: the 8 records of a window are staged in the ring (two 2 KB halves, the next window's copy in
+    // flight while this one computes); R is re-based so that step k of the window reads ring step (half * 8 + k - j0).
+    auto stage = [&](int j0, int len, int half) {
+        if (PF) {
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int q = 0; q < kWin / 2; ++q) {
+                const int st = 2 * q + (lane >> 4);
+                if (st < len)
+                    q_cpa16(ring + (half * kWin + st) * kGrecStep + (lane & 15) * 4,
+                            ggrp + (size_t)(j0 + st) * kGrecStep + (lane & 15) * 4);
+            }
+            q_cpa_commit();
+        }
+    };
+    auto rebased = [&](int j0, int half) -> Recs<SS> {
+        Recs<SS> W = R;
+        if (PF) {
+            const int d = (half * kWin - j0) * kGrecStep;
+            W.pA0 += d; W.pB0 += d; W.pA1 += d; W.pB1 += d;
+        }
+        return W;
+    };
     if (warp == 0) {
+        int half = 0;
+        stage(M, N - M >= kWin ? kWin : 4, 0);
         for (int w = 0; w < g.nckB; ++w) {
             const int j0 = M + w * kWin;
-            if (N - j0 >= kWin) window_alpha<kWin>(r, grec, R, ck, g.nckA + w, j0, L, x);
-            else                window_alpha<4>(r, grec, R, ck, g.nckA + w, j0, L, x);
+            if (PF) {
+                __syncwarp();
+                const int jn = j0 + kWin;
+                if (w + 1 < g.nckB) stage(jn, N - jn >= kWin ? kWin : 4, half ^ 1); else q_cpa_commit();
+                q_cpa_wait<1>();
+                __syncwarp();
+            }
+            const Recs<SS> W = rebased(j0, half);
+            if (N - j0 >= kWin) window_alpha<kWin, SS>(r, grec, W, ck, g.nckA + w, j0, L, x);
+            else                window_alpha<4, SS>(r, grec, W, ck, g.nckA + w, j0, L, x);
+            half ^= 1;
         }
     } else {
-        for (int w = g.nckA - 1; w >= 0; --w)
-            window_beta(r, grec, R, ck, w, w * kWin, L, x);
+        int half = 0;
+        stage((g.nckA - 1) * kWin, kWin, 0);
+        for (int w = g.nckA - 1; w >= 0; --w) {
+            if (PF) {
+                __syncwarp();
+                if (w > 0) stage((w - 1) * kWin, kWin, half ^ 1); else q_cpa_commit();
+                q_cpa_wait<1>();
+                __syncwarp();
+            }
+            const Recs<SS> W = rebased(w * kWin, half);
+            window_beta<SS>(r, grec, W, ck, w, w * kWin, L, x);
+            half ^= 1;
+        }
     }
+    if (PF) q_cpa_wait<0>();
     __syncthreads();
 }
 
@@ -472,7 +598,7 @@ __device__ __forceinline__ double2 make_extrinsic(const float4 uv, double YA, do
     return make_double2(ea, eb);
 }
 
-template <bool SISO_ONLY, bool TMEM>
+template <bool SISO_ONLY, bool TMEM, bool GREC = false>
 __global__ void __launch_bounds__(kMaxCtaThreads)
 quad_kernel(const QuadArgs A)
 {
@@ -494,13 +620,19 @@ quad_kernel(const QuadArgs A)
     // ---- shared memory carve-up -------------------------------------------------
     int16_t *tab = reinterpret_cast<int16_t *>(smem_raw);
     const int tab_bytes = ((7 * N * 2 + 15) / 16) * 16;
-    float *gam = reinterpret_cast<float *>(smem_raw + tab_bytes);
     const int FR = g.frames;                         // frames this CTA decodes at a time
     const int areas = FR + (FR < 8 * g.groups);      // idle quads (frame slot >= FR) share one scratch area
-    float *ckbuf = gam + areas * g.rec_stride;
+    // GREC (long frames): the records of 32 frames do not fit in shared memory, so they live in this CTA's slice of
+    // the global workspace and reach the SM through L1 (which gets the shared memory this geometry does not use) and
+    // L2; only this CTA reads or writes its slice, so the SM's own L1 stays coherent with it.
+    float *smf = reinterpret_cast<float *>(smem_raw + tab_bytes);
+    float *gam = smf;
+    if constexpr (GREC) gam = A.grec + (size_t)blockIdx.x * areas * g.rec_stride;
+    float *ckbuf = GREC ? smf : gam + areas * g.rec_stride;
     float *xch = ckbuf + (TMEM ? 0 : areas * g.ck_stride);
     int *flags = reinterpret_cast<int *>(xch + 4 * g.groups * kXchFloats);
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(flags + 64);
+    float *rings = reinterpret_cast<float *>(flags + 68);            // GREC: one record ring per recursion warp
     unsigned char *hb = reinterpret_cast<unsigned char *>(gam);   // hard-bit pairs: the records are dead by then
     if (TMEM && wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -522,6 +654,9 @@ quad_kernel(const QuadArgs A)
     const unsigned ytaddr = tmem_base + (((unsigned)(wid & 3) * 32u) << 16) +
                             4u * (g.nckA + g.nckB) + 4u * g.y_slots * (unsigned)(wid >> 2);
     const int P = FR * N;                   // (frame, step) positions of this CTA, dealt out flat
+    // positions per thread whose loads are issued together in prep / epilogue: with the records in global memory these
+    // phases are a string of L2 / HBM round trips on 14 warps, so twice as many are kept in flight
+    constexpr int KB = GREC ? 2 * kBatch : kBatch;
     const unsigned magic = g.magic;
     const int16_t *t_perm = tab, *t_inv = tab + N, *t_offA = tab + 2 * N;
 
@@ -553,15 +688,15 @@ quad_kernel(const QuadArgs A)
             __syncthreads();   // tables loaded / previous phase finished with gam, Le
             const long long t0 = clock64();
             // ---- prep: gather, a-priori add, branch-metric records ------------------
-            // kBatch positions per thread are loaded before any is consumed, so the
+            // KB positions per thread are loaded before any is consumed, so the
             // dependent smem-index -> L2 gather round trips overlap.
-            for (int it = 0; it * kBatch * NT < P; ++it) {       // warp-uniform trip count
-                const int i0 = tid + it * kBatch * NT;
-                float sA[kBatch], sB[kBatch], pW[kBatch], pY[kBatch];
-                double2 La[kBatch];
+            for (int it = 0; it * KB * NT < P; ++it) {       // warp-uniform trip count
+                const int i0 = tid + it * KB * NT;
+                float sA[KB], sB[KB], pW[KB], pY[KB];
+                double2 La[KB];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                for (int u = 0; u < KB; ++u) {
+                    int f, k; const int i = i0 + u * NT; pos_of<GREC>(i, N, magic, f, k);
                     const long long frame = frame0 + f;
                     sA[u] = sB[u] = pW[u] = pY[u] = 0.f;
                     La[u] = make_double2(0.0, 0.0);
@@ -595,8 +730,8 @@ quad_kernel(const QuadArgs A)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                for (int u = 0; u < KB; ++u) {
+                    int f, k; const int i = i0 + u * NT; pos_of<GREC>(i, N, magic, f, k);
                     // computed unconditionally (one basic block, so the independent
                     // float64 chains of the batch interleave); only the stores are guarded
                     const double YA = __dadd_rn((double)sA[u], La[u].x);   // Lc_A[k] + La_A[k] (:135)
@@ -604,14 +739,14 @@ quad_kernel(const QuadArgs A)
                     float4 lo4, hi4;
                     make_record(k, YA, YB, pW[u], pY[u], lo4, hi4);
                     if (i < P) {
-                        float *rec = gam + f * g.rec_stride + k * 8;
+                        float *rec = GREC ? gam + ((size_t)(f >> 3) * N + k) * kGrecStep + (f & 7) * 8 : gam + f * g.rec_stride + k * 8;
                         *reinterpret_cast<float4 *>(rec) = lo4;
                         *reinterpret_cast<float4 *>(rec + 4) = hi4;
                         if (!YTMEM) __stcg(Yb + (size_t)f * N + k, make_double2(YA, YB));
                     }
-                    if (YTMEM)          // Y stays on chip: this thread's TMEM lane, slot = it*kBatch + u
+                    if (YTMEM)          // Y stays on chip: this thread's TMEM lane, slot = it*KB + u
                         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                                     ::"r"(ytaddr + 4u * (it * kBatch + u)), "r"(__double2loint(YA)), "r"(__double2hiint(YA)),
+                                     ::"r"(ytaddr + 4u * (it * KB + u)), "r"(__double2loint(YA)), "r"(__double2hiint(YA)),
                                        "r"(__double2loint(YB)), "r"(__double2hiint(YB)) : "memory");
                 }
             }
@@ -623,7 +758,7 @@ quad_kernel(const QuadArgs A)
                 Ckpt<TMEM> ck;
                 if constexpr (TMEM) ck.taddr = tmem_base + (((unsigned)(wid & 3) * 32u) << 16);
                 else ck.base = ckbuf + L.q * g.ck_stride + 4 * L.p;
-                siso_core(g, gam, ck, xch, warp, xslot, L, t2);
+                siso_core<GREC>(g, gam, ck, xch, rings, warp, xslot, L, t2);
             } else {
                 __syncthreads();
                 t2 = clock64();
@@ -631,29 +766,29 @@ quad_kernel(const QuadArgs A)
             }
             const long long t3 = clock64();
             // ---- epilogue: extrinsic LLRs (float64) ---------------------------------
-            for (int it = 0; it * kBatch * NT < P; ++it) {
-                const int i0 = tid + it * kBatch * NT;
-                double2 Y[kBatch];
-                float4 uv[kBatch];
+            for (int it = 0; it * KB * NT < P; ++it) {
+                const int i0 = tid + it * KB * NT;
+                double2 Y[KB];
+                float4 uv[KB];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                for (int u = 0; u < KB; ++u) {
+                    int f, k; const int i = i0 + u * NT; pos_of<GREC>(i, N, magic, f, k);
                     Y[u] = make_double2(0.0, 0.0); uv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i < P && frame0 + f < A.B) {
                         if (!YTMEM) Y[u] = __ldcg(Yb + (size_t)f * N + k);
-                        uv[u] = *reinterpret_cast<const float4 *>(gam + f * g.rec_stride + k * 8);
+                        uv[u] = *reinterpret_cast<const float4 *>(GREC ? gam + ((size_t)(f >> 3) * N + k) * kGrecStep + (f & 7) * 8 : gam + f * g.rec_stride + k * 8);
                     }
                     if (YTMEM) {
                         int a, b, c, d;
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(ytaddr + 4u * (it * kBatch + u)) : "memory");
+                                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(ytaddr + 4u * (it * KB + u)) : "memory");
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         Y[u] = make_double2(__hiloint2double(b, a), __hiloint2double(d, c));
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    int f, k; const int i = i0 + u * NT; split_pos(i, N, magic, f, k);
+                for (int u = 0; u < KB; ++u) {
+                    int f, k; const int i = i0 + u * NT; pos_of<GREC>(i, N, magic, f, k);
                     const long long frame = frame0 + f;
                     const double2 e = make_extrinsic(uv[u], Y[u].x, Y[u].y, sf);
                     if (i < P && frame < A.B) {
@@ -770,6 +905,7 @@ static size_t quad_smem_bytes(const QuadGeom &g)
 {
     const int areas = g.frames + (g.frames < 8 * g.groups);
     size_t tab = ((size_t)7 * g.N * 2 + 15) / 16 * 16;
+    if (g.grec) return tab + (size_t)4 * g.groups * kXchFloats * 4 + 68 * 4 + (size_t)2 * g.groups * kRingSteps * kGrecStep * 4;
     size_t fl = (size_t)areas * g.rec_stride + (g.use_tmem ? 0 : (size_t)areas * g.ck_stride) +
                 4 * g.groups * kXchFloats;
     return tab + fl * 4 + 68 * 4;
@@ -857,23 +993,61 @@ int quad_configure(Codec &c)
     }
     if (occ < 1) return B200DVB_ENOSPEC;
     g.ctas_per_sm = occ;
+    // Long frames: when shared memory holds the records of fewer than three groups (N >= 296: 2 x 8 frames at N=424, 8
+    // at N=752: two recursion warps on an SM), a second geometry keeps the records in global memory and runs the full
+    // four groups (32 frames, 8 recursion warps) per SM.
+    c.geom_g = QuadGeom{};
+    if (g.frames <= 16 && 4 * (g.nckA + g.nckB) <= 512) {
+        QuadGeom t = g;
+        t.grec = 1; t.use_tmem = 1; t.groups = 4; t.frames = 32; t.y_slots = 0;   // (Y stays in global memory: KB != kBatch)
+        t.threads = kMaxCtaThreads;
+        t.tmem_cols = 32;
+        while (t.tmem_cols < 4 * (t.nckA + t.nckB)) t.tmem_cols *= 2;
+        t.smem_bytes = quad_smem_bytes(t);
+        B2_CUDA(cudaFuncSetAttribute(quad_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        // the shared memory this geometry leaves unused is worth more as L1 for the records
+        B2_CUDA(cudaFuncSetAttribute(quad_kernel<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)((t.smem_bytes * 100 + cap - 1) / cap) + 4));
+        int og = 0;
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&og, quad_kernel<false, true, true>, t.threads, t.smem_bytes));
+        if (og > 512 / t.tmem_cols) og = 512 / t.tmem_cols;
+        if (og > 1) og = 1;
+        if (og >= 1) { t.ctas_per_sm = og; c.geom_g = t; }
+    }
     return B200DVB_OK;
 }
 
-static int grid_for(const Codec &c, int B)
+// Geometry that serves a full decode of B frames: the global-record one as soon as the batch exceeds two waves of the
+// shared-memory one (below that the shared-memory geometry spreads the frames over more SMs: at N=752 two waves of
+// 8 frames per SM take 3.7 ms, half the SMs with 32 frames each 4.1 ms).  A pure function of (codec, B): the workspace
+// query and the launch agree.
+static const QuadGeom &decode_geom(const Codec &c, int B)
 {
-    const int groups = (B + c.geom.frames - 1) / c.geom.frames;
-    const int cap = c.num_sms * c.geom.ctas_per_sm;
+    if (c.geom_g.frames > 0 && (long long)B > 2ll * c.num_sms * c.geom.ctas_per_sm * c.geom.frames) return c.geom_g;
+    return c.geom;
+}
+
+static int grid_for(const Codec &c, const QuadGeom &g, int B)
+{
+    const int groups = (B + g.frames - 1) / g.frames;
+    const int cap = c.num_sms * g.ctas_per_sm;
     return groups < cap ? groups : cap;
+}
+static size_t grec_floats(const QuadGeom &g, int grid)
+{
+    const int areas = g.frames + (g.frames < 8 * g.groups);
+    return g.grec ? (size_t)grid * areas * g.rec_stride : 0;
 }
 
 size_t decode_workspace_bytes(const Codec &c, int B)
 {
-    return (size_t)3 * grid_for(c, B) * c.geom.frames * c.N * sizeof(double2) + 256;
+    const QuadGeom &g = decode_geom(c, B);
+    const int grid = grid_for(c, g, B);
+    return (size_t)3 * grid * g.frames * c.N * sizeof(double2) + grec_floats(g, grid) * sizeof(float) + 512;
 }
 size_t siso_workspace_bytes(const Codec &c, int B)
 {
-    return (size_t)grid_for(c, B) * c.geom.frames * c.N * sizeof(double2) + 256;
+    return (size_t)grid_for(c, c.geom, B) * c.geom.frames * c.N * sizeof(double2) + 256;
 }
 
 static inline unsigned char *align256(void *p)
@@ -887,11 +1061,12 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
 {
     if (B == 0) return B200DVB_OK;
     if (ws_bytes < decode_workspace_bytes(c, B)) return B200DVB_ENOMEM;
-    const int grid = grid_for(c, B);
-    const size_t per = (size_t)grid * c.geom.frames * c.N;
+    const QuadGeom &G = decode_geom(c, B);
+    const int grid = grid_for(c, G, B);
+    const size_t per = (size_t)grid * G.frames * c.N;
     QuadArgs A{};
-    A.g = c.geom; A.B = B; A.iterations = c.iterations;
-    A.n_groups = (B + c.geom.frames - 1) / c.geom.frames;
+    A.g = G; A.B = B; A.iterations = c.iterations;
+    A.n_groups = (B + G.frames - 1) / G.frames;
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed;
     A.ref_bits = ref_bits; A.counters = counters;
@@ -901,8 +1076,10 @@ int launch_decode(const Codec &c, int B, const float *llr, long long llr_stride,
     A.timed = c.opt_phase_timers;
     A.Le1 = reinterpret_cast<double2 *>(align256(ws));
     A.Le2 = A.Le1 + per; A.Y = A.Le2 + per;
-    if (c.geom.use_tmem) quad_kernel<false, true><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
-    else                 quad_kernel<false, false><<<grid, c.geom.threads, c.geom.smem_bytes, s>>>(A);
+    A.grec = reinterpret_cast<float *>(align256(A.Y + per));
+    if (G.grec)          quad_kernel<false, true, true><<<grid, G.threads, G.smem_bytes, s>>>(A);
+    else if (G.use_tmem) quad_kernel<false, true><<<grid, G.threads, G.smem_bytes, s>>>(A);
+    else                 quad_kernel<false, false><<<grid, G.threads, G.smem_bytes, s>>>(A);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }
@@ -913,7 +1090,7 @@ int launch_siso(const Codec &c, int B, const float *Lc_A, const float *Lc_B, con
 {
     if (B == 0) return B200DVB_OK;
     if (ws_bytes < siso_workspace_bytes(c, B)) return B200DVB_ENOMEM;
-    const int grid = grid_for(c, B);
+    const int grid = grid_for(c, c.geom, B);
     QuadArgs A{};
     A.g = c.geom; A.B = B; A.iterations = 1;
     A.n_groups = (B + c.geom.frames - 1) / c.geom.frames;

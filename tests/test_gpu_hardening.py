@@ -24,7 +24,8 @@ def _mc(g, B, ebn0_db, seed):
 
 @pytest.mark.parametrize("kernel,N,rate,B", [("tpf", 212, '1/3', 100_000), ("quad", 212, '1/3', 20_000),
                                              ("tpf", 48, '1/2', 100_000), ("quad", 424, '1/3', 6_000),
-                                             ("lat", 212, '1/3', 20_000), ("lat", 752, '1/2', 3_000)])
+                                             ("lat", 212, '1/3', 20_000), ("lat", 752, '1/2', 3_000),
+                                             ("quad", 752, '1/2', 6_000), ("quad", 848, '1/3', 5_000)])
 def test_randomised_large_batch_vs_oracle(kernel, N, rate, B):
     """10^5 DISTINCT frames (device Philox source, Eb/N0 2 dB) through the CUDA decoder and through the C oracle
     on every host thread: every hard decision must agree.  Distinct inputs in every tile and wave are what a

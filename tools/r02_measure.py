@@ -82,6 +82,14 @@ if "long" in which:
         best, med = timeit(lambda: c.decode_batch(llr, ref_bits=info, counters=cnt, out="none"), n=3, warm=1)
         fps = B / (best * 1e-3); acs = 320 * N * 2 * 8
         print(f"N={N:4d} R={rate}: wave={wave:5d} B={B:6d} {best:8.2f} ms  {fps/1e6:7.3f} Mframes/s  {fps*2*N/1e9:6.3f} Gbit/s  {fps*acs/(64*148*1.965e9)*100:5.1f}% of ALU roofline")
+        if N > 212:
+            c.handle.set_option(_lib.OPT_PHASE_TIMERS, 1)
+            ph = np.zeros(8); lib.b200dvb_debug_phase_cycles(_lib.host_ptr(ph), 1)
+            c.decode_batch(llr, out="none"); torch.cuda.synchronize()
+            lib.b200dvb_debug_phase_cycles(_lib.host_ptr(ph), 1)
+            c.handle.set_option(_lib.OPT_PHASE_TIMERS, 0)
+            tot = ph[5] if ph[5] else 1.0
+            print("        phases (share of CTA cycles): prep %.1f%%  recursion in %.1f%%  out %.1f%%  epilogue %.1f%%  hard decision %.1f%%" % tuple(100 * ph[i] / tot for i in range(5)))
         del info, llr
 
 if "demap" in which:

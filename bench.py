@@ -555,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
         g752 = c752.decode_batch(l752h)
         n752 = {"info_gbit_per_s": B752 * c752.k_info / (ms752 * 1e-3) / 1e9, "frames": B752, "ms": ms752,
                 "roofline": {"bound": "alu", "achieved": a752, "peak": peak, "unit": "TACS/s", "frac": a752 / peak, "traffic": None},
-                "kernel": "quad_kernel (8 frames per SM: records of longer frames do not fit on chip for the thread-per-frame mapping)",
+                "kernel": "quad_kernel, global-record geometry (32 frames per SM, records in global memory fed through a cp.async ring: the records of longer frames do not fit on chip)",
                 "cpu_baseline": {"value": len(l752h) * c752.k_info / dt752 / 1e9, "unit": "Gbit/s", "kind": kind752,
                                  "cores": os.cpu_count(), "sample": f"{len(l752h)} frames in {dt752:.2f} s; {det752}"},
                 "matches_cpu_arm": bool(np.array_equal(g752, dec752)),

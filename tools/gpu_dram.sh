@@ -10,6 +10,8 @@ timeout 300 python tools/nii_prof_cmd.py 37888 nii > gpurun_out/dram_plain_nii.l
 timeout 900 $NCU -k regex:nii_kernel -s 1 -c 1 -f -o gpurun_out/prof_dram_nii python tools/nii_prof_cmd.py 37888 nii > gpurun_out/ncu_dram_nii.log 2>&1
 timeout 300 python tools/nii_prof_cmd.py 4736 double-pass 752 1/2 > gpurun_out/dram_plain_quad.log 2>&1 &&
 timeout 900 $NCU -k regex:quad_kernel -s 1 -c 1 -f -o gpurun_out/prof_dram_quad752 python tools/nii_prof_cmd.py 4736 double-pass 752 1/2 > gpurun_out/ncu_dram_quad.log 2>&1
+timeout 300 python tools/nii_prof_cmd.py 16 double-pass 212 1/3 lat > gpurun_out/dram_plain_lat.log 2>&1 &&
+timeout 900 $NCU -k regex:lat_kernel -s 1 -c 1 -f -o gpurun_out/prof_dram_lat python tools/nii_prof_cmd.py 16 double-pass 212 1/3 lat > gpurun_out/ncu_dram_lat.log 2>&1
 timeout 300 python tools/wf_perf.py demap > gpurun_out/dram_plain_demap.log 2>&1 &&
 timeout 900 $NCU -k regex:demap -s 6 -c 6 -f -o gpurun_out/prof_dram_demap python tools/wf_perf.py demap > gpurun_out/ncu_dram_demap.log 2>&1
 timeout 300 python tools/wf_perf.py once > gpurun_out/dram_plain_mf.log 2>&1 &&

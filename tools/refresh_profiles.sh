@@ -3,10 +3,10 @@
 set -e
 cd "$(dirname "$0")/.."
 python tools/make_traffic_json.py > /dev/null
-for k in tpf nii quad752 mf demap; do python tools/ncu_key_metrics.py gpurun_out/prof_dram_$k.ncu-rep > /tmp/k_$k.txt 2>&1; done
+for k in tpf nii quad752 lat mf demap; do python tools/ncu_key_metrics.py gpurun_out/prof_dram_$k.ncu-rep > /tmp/k_$k.txt 2>&1; done
 cp /tmp/k_tpf.txt profiles/r02_tpf_kernel_ncu.txt; cp /tmp/k_nii.txt profiles/r02_nii_kernel_ncu.txt
-cp /tmp/k_quad752.txt profiles/r02_quad_kernel_n752_ncu.txt; cp /tmp/k_mf.txt profiles/r02_waveform_ncu.txt; cp /tmp/k_demap.txt profiles/r02_demap_ncu.txt
-cp gpurun_out/r02_final_gpu_tests.txt gpurun_out/r02_launches.csv gpurun_out/r02_mc_source_perf.txt profiles/
+cp /tmp/k_quad752.txt profiles/r02_quad_kernel_n752_ncu.txt; cp /tmp/k_lat.txt profiles/r02_lat_kernel_ncu.txt; cp /tmp/k_mf.txt profiles/r02_waveform_ncu.txt; cp /tmp/k_demap.txt profiles/r02_demap_ncu.txt
+cp gpurun_out/r02_final_gpu_tests.txt gpurun_out/r02_launches.csv gpurun_out/r02_mc_source_perf.txt gpurun_out/r02_latency.txt gpurun_out/r02_long.txt profiles/
 python - <<'PY'
 import csv, collections
 rows=list(csv.reader(open('gpurun_out/r02_launches.csv')))

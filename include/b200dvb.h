@@ -224,8 +224,10 @@ int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
 int b200dvb_debug_nii_cycles(double *out8_h, int reset);
 
 /* Process-wide development switches (never needed in production).
- *   B200DVB_DBG_MF_VARIANT  matched-filter kernel: 0 = default, 1 = double-buffered cp.async staging, 2 = round-1 kernel */
+ *   B200DVB_DBG_MF_VARIANT  matched-filter kernel: 0 = default, 1 = double-buffered cp.async staging, 2 = round-1 kernel
+ *   B200DVB_DBG_MAP_VARIANT complex64 mapper: 0 = per-order choice, 1 = one symbol per lane, 2 = four consecutive symbols per lane */
 #define B200DVB_DBG_MF_VARIANT 1
+#define B200DVB_DBG_MAP_VARIANT 2
 int b200dvb_debug_set_option(int option, int value);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the

@@ -462,6 +462,10 @@ int b200dvb_debug_set_option(int option, int value)
         if (value < 0 || value > 2) return B200DVB_EINVAL;
         set_mf_variant(value);
         return B200DVB_OK;
+    case B200DVB_DBG_MAP_VARIANT:
+        if (value < 0 || value > 2) return B200DVB_EINVAL;
+        set_map_variant(value);
+        return B200DVB_OK;
     default: return B200DVB_EINVAL;
     }
 }

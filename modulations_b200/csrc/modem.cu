@@ -53,6 +53,143 @@ __global__ void map_kernel(size_t n, int bps, const uint8_t *__restrict__ bits,
     }
 }
 
+// The same mapping for complex64 output, written for the memory system: the generic kernel above keeps ONE symbol per
+// thread in flight behind a dependent byte load (2.6 symbols per clock and SM: 53 - 64 % of the HBM roofline).  Here a
+// thread takes FOUR CONSECUTIVE symbols at a time — 4 BPS bit-bytes = BPS aligned words in (one to three vector loads,
+// no symbol straddles the group), 32 bytes out (two 16-byte stores; a warp writes 1 KB contiguous) — with kMapU such
+// groups in flight, and gathers a label (first bit = MSB, sdr_modem.py:260-274) from the byte LSBs with one multiply:
+// ((w & 0x01010101) * 0x08040201) >> 24 = 8 b0 + 4 b1 + 2 b2 + b3 (the partial products occupy distinct bits).
+constexpr int kMapU = 2;
+
+__device__ __forceinline__ unsigned lab4(unsigned w) { return ((w & 0x01010101u) * 0x08040201u) >> 24; }
+
+template <int BPS>
+__device__ __forceinline__ void load_words(const uint8_t *__restrict__ p, unsigned (&w)[BPS])
+{
+    if constexpr (BPS == 1) w[0] = *reinterpret_cast<const unsigned *>(p);
+    else if constexpr (BPS == 2) { const uint2 v = *reinterpret_cast<const uint2 *>(p); w[0] = v.x; w[1] = v.y; }
+    else if constexpr (BPS == 3) {
+        const unsigned *q = reinterpret_cast<const unsigned *>(p);
+        w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
+    } else if constexpr (BPS == 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (BPS == 6) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(p);
+        const uint2 a = q[0], b = q[1], c = q[2];
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+    } else {
+        static_assert(BPS == 8, "orders of the reference: 1, 2, 3, 4, 6, 8 bits per symbol");
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        const uint4 a = q[0], b = q[1];
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+}
+// the four bytes starting at byte Q of the group (compile-time Q; bytes past the group read as 0)
+template <int BPS, int Q>
+__device__ __forceinline__ unsigned bytes4(const unsigned (&w)[BPS])
+{
+    constexpr int i = Q >> 2, sh = 8 * (Q & 3);
+    const unsigned lo = i < BPS ? w[i < BPS ? i : 0] : 0u, hi = i + 1 < BPS ? w[i + 1 < BPS ? i + 1 : 0] : 0u;
+    return sh ? __funnelshift_r(lo, hi, sh) : lo;
+}
+template <int BPS, int J>
+__device__ __forceinline__ unsigned group_label(const unsigned (&w)[BPS])
+{
+    constexpr int Q = J * BPS;
+    if constexpr (BPS <= 4) {
+        constexpr unsigned mask = BPS == 4 ? 0x01010101u : (1u << (8 * BPS)) - 1u;
+        return lab4(bytes4<BPS, Q>(w) & mask) >> (4 - BPS);
+    } else {
+        constexpr unsigned mask = BPS == 8 ? 0x01010101u : (1u << (8 * (BPS - 4))) - 1u;
+        return (lab4(bytes4<BPS, Q>(w)) << (BPS - 4)) | (lab4(bytes4<BPS, Q + 4>(w) & mask) >> (8 - BPS));
+    }
+}
+
+template <int BPS>
+__global__ void __launch_bounds__(kThreads)
+map_words_kernel(size_t n, const uint8_t *__restrict__ bits, const double *__restrict__ table, float2 *__restrict__ iq)
+{
+    __shared__ float2 tab[1 << BPS];
+    for (int i = threadIdx.x; i < (1 << BPS); i += blockDim.x)       // complex128 -> complex64 rounds like np.array(.., complex64)
+        tab[i] = make_float2((float)table[2 * i], (float)table[2 * i + 1]);
+    __syncthreads();
+    const size_t groups = n >> 2;                                    // whole groups of 4 symbols
+    const size_t stride = (size_t)gridDim.x * blockDim.x * kMapU;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * kMapU + threadIdx.x; base < groups; base += stride) {
+        unsigned w[kMapU][BPS];
+#pragma unroll
+        for (int u = 0; u < kMapU; ++u) {
+            const size_t g = base + (size_t)u * blockDim.x;
+            if (g < groups) load_words<BPS>(bits + g * (4 * BPS), w[u]);
+            else
+#pragma unroll
+                for (int q = 0; q < BPS; ++q) w[u][q] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kMapU; ++u) {
+            const size_t g = base + (size_t)u * blockDim.x;
+            if (g < groups) {
+                const float2 s0 = tab[group_label<BPS, 0>(w[u])], s1 = tab[group_label<BPS, 1>(w[u])];
+                const float2 s2 = tab[group_label<BPS, 2>(w[u])], s3 = tab[group_label<BPS, 3>(w[u])];
+                // one 256-bit store (sm_100: STG.E.ENL2.256): the lane's four symbols are exactly one 32-byte sector;
+                // as two 16-byte stores every sector was written in two partial pieces (59 - 74 % instead of 8x %)
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(iq + 4 * g),
+                             "l"(*reinterpret_cast<const unsigned long long *>(&s0)), "l"(*reinterpret_cast<const unsigned long long *>(&s1)),
+                             "l"(*reinterpret_cast<const unsigned long long *>(&s2)), "l"(*reinterpret_cast<const unsigned long long *>(&s3)) : "memory");
+            }
+        }
+    }
+    // the last n % 4 symbols, bit by bit
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = 4 * groups + threadIdx.x;
+        unsigned lab = 0;
+        for (int b = 0; b < BPS; ++b) lab = (lab << 1) | (bits[i * BPS + b] & 1u);
+        iq[i] = tab[lab];
+    }
+}
+
+// One symbol per lane and store (8 bytes per lane, 256 contiguous bytes per warp store), kSymU symbols per thread in
+// flight: the symbol's BPS bit-bytes are one aligned load for BPS = 1, 2, 4, 8.
+constexpr int kSymU = 4;
+template <int BPS>
+__device__ __forceinline__ unsigned load_label(const uint8_t *__restrict__ bits, size_t i)
+{
+    const size_t o = i * BPS;
+    if constexpr (BPS == 1) return bits[o] & 1u;
+    else if constexpr (BPS == 2) {
+        const unsigned w = *reinterpret_cast<const uint16_t *>(bits + o);
+        return ((w & 1u) << 1) | ((w >> 8) & 1u);
+    } else if constexpr (BPS == 4) return lab4(*reinterpret_cast<const unsigned *>(bits + o));
+    else {
+        static_assert(BPS == 8, "aligned orders only");
+        const uint2 w = *reinterpret_cast<const uint2 *>(bits + o);
+        return (lab4(w.x) << 4) | lab4(w.y);
+    }
+}
+template <int BPS>
+__global__ void __launch_bounds__(kThreads)
+map_sym_kernel(size_t n, const uint8_t *__restrict__ bits, const double *__restrict__ table, float2 *__restrict__ iq)
+{
+    __shared__ float2 tab[1 << BPS];
+    for (int i = threadIdx.x; i < (1 << BPS); i += blockDim.x)
+        tab[i] = make_float2((float)table[2 * i], (float)table[2 * i + 1]);
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x * kSymU;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * kSymU + threadIdx.x; base < n; base += stride) {
+        unsigned lab[kSymU];
+#pragma unroll
+        for (int u = 0; u < kSymU; ++u) {
+            const size_t i = base + (size_t)u * blockDim.x;
+            lab[u] = i < n ? load_label<BPS>(bits, i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kSymU; ++u) {
+            const size_t i = base + (size_t)u * blockDim.x;
+            if (i < n) iq[i] = tab[lab[u]];
+        }
+    }
+}
+
 template <typename InT>
 __global__ void hard_kernel(size_t n, int bps, const typename Cplx<InT>::type *__restrict__ iq,
                             const double *__restrict__ table, uint8_t *__restrict__ bits)
@@ -312,9 +449,30 @@ int modem_build_pwl(Modem &m)
     return B200DVB_OK;
 }
 
+static int g_map_variant = 0;      // development: 0 = per-order choice, 1 = one symbol per lane, 2 = four per lane
+void set_map_variant(int v) { g_map_variant = v; }
+
 int launch_map(const Modem &m, size_t n, const uint8_t *bits, void *iq, int out_f64, cudaStream_t s)
 {
     if (n == 0) return B200DVB_OK;
+    // complex64 out, both pointers 32-byte aligned, one of the six orders of the reference: the word-load kernel;
+    // anything else: the generic one
+    if (!out_f64 && ((reinterpret_cast<uintptr_t>(bits) | reinterpret_cast<uintptr_t>(iq)) & 31) == 0) {
+        const int gridg = grid_for((n + 3) / 4, kThreads * kMapU, 8), grids = grid_for(n, kThreads * kSymU, 8);
+        float2 *o = (float2 *)iq;
+        const bool grp = g_map_variant == 2 || (g_map_variant == 0 && m.bps >= 3);   // measured per order: profiles/r02_mapper.txt
+        switch (m.bps) {
+        case 1: if (grp) map_words_kernel<1><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); else map_sym_kernel<1><<<grids, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        case 2: if (grp) map_words_kernel<2><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); else map_sym_kernel<2><<<grids, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        case 4: if (grp) map_words_kernel<4><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); else map_sym_kernel<4><<<grids, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        case 8: if (grp) map_words_kernel<8><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); else map_sym_kernel<8><<<grids, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        case 3: map_words_kernel<3><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        case 6: map_words_kernel<6><<<gridg, kThreads, 0, s>>>(n, bits, m.d_table64, o); break;
+        default: map_kernel<float><<<grid_for(n, kThreads, 8), kThreads, 0, s>>>(n, m.bps, bits, m.d_table64, o); break;
+        }
+        B2_CUDA(cudaGetLastError());
+        return B200DVB_OK;
+    }
     const int grid = grid_for(n, kThreads, 8);
     if (out_f64) map_kernel<double><<<grid, kThreads, 0, s>>>(n, m.bps, bits, m.d_table64, (double2 *)iq);
     else         map_kernel<float><<<grid, kThreads, 0, s>>>(n, m.bps, bits, m.d_table64, (float2 *)iq);

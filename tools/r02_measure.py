@@ -105,7 +105,10 @@ if "demap" in which:
         del out
         bits = torch.randint(0, 2, (n * m.bps,), dtype=torch.uint8, device="cuda")
         sy = torch.empty(n, dtype=torch.complex64, device="cuda")
-        best, med = timeit(lambda: lib.b200dvb_map(m.h, n, _lib.ptr(bits), _lib.ptr(sy), 0, _lib.stream_ptr()))
         by = n * (m.bps + 8)
-        print(f"map   {name:7s}: {med:.3f} ms  {n/med/1e6:.1f} Gsym/s  {by/med/1e6:.0f} GB/s (uint8 bit per byte in) = {by/med/1e6/6545.3*100:.1f}%")
+        for var, what in ((1, "one symbol per lane"), (2, "four per lane, 256-bit store"), (0, "shipped choice")):
+            if var == 1 and m.bps in (3, 6): continue
+            _lib.check(lib.b200dvb_debug_set_option(2, var), "dbg")
+            best, med = timeit(lambda: lib.b200dvb_map(m.h, n, _lib.ptr(bits), _lib.ptr(sy), 0, _lib.stream_ptr()))
+            print(f"map   {name:7s} [{what:28s}]: {med:.3f} ms  {n/med/1e6:.1f} Gsym/s  {by/med/1e6:.0f} GB/s (uint8 bit per byte in) = {by/med/1e6/6545.3*100:.1f}%")
         del bits, sy

@@ -1017,14 +1017,19 @@ int quad_configure(Codec &c)
     return B200DVB_OK;
 }
 
-// Geometry that serves a full decode of B frames: the global-record one as soon as the batch exceeds two waves of the
-// shared-memory one (below that the shared-memory geometry spreads the frames over more SMs: at N=752 two waves of
-// 8 frames per SM take 3.7 ms, half the SMs with 32 frames each 4.1 ms).  A pure function of (codec, B): the workspace
-// query and the launch agree.
+// Geometry that serves a full decode of B frames: whichever needs less time for its waves.  One wave of the
+// global-record geometry (32 frames per SM) takes 2.3 x as long as one of the shared-memory geometry with 8 frames per
+// SM (N=752: 4.15 ms against 1.84 ms) and 1.85 x one with 16 frames per SM (N=424: 2.08 against 1.15 ms;
+// profiles/r02_long.txt), so small batches, which the shared-memory geometry spreads over more SMs, stay there.  A pure
+// function of (codec, B): the workspace query and the launch agree.
 static const QuadGeom &decode_geom(const Codec &c, int B)
 {
-    if (c.geom_g.frames > 0 && (long long)B > 2ll * c.num_sms * c.geom.ctas_per_sm * c.geom.frames) return c.geom_g;
-    return c.geom;
+    if (c.geom_g.frames <= 0) return c.geom;
+    const long long sw = (long long)c.num_sms * c.geom.ctas_per_sm * c.geom.frames;
+    const long long gw = (long long)c.num_sms * c.geom_g.ctas_per_sm * c.geom_g.frames;
+    const long long waves_s = (B + sw - 1) / sw, waves_g = (B + gw - 1) / gw;
+    const long long r100 = c.geom.frames <= 8 ? 230 : 185;
+    return waves_g * r100 < waves_s * 100 ? c.geom_g : c.geom;
 }
 
 static int grid_for(const Codec &c, const QuadGeom &g, int B)

@@ -23,7 +23,7 @@ def _mc(g, B, ebn0_db, seed):
 
 
 @pytest.mark.parametrize("kernel,N,rate,B", [("tpf", 212, '1/3', 100_000), ("quad", 212, '1/3', 20_000),
-                                             ("tpf", 48, '1/2', 100_000), ("quad", 424, '1/3', 6_000),
+                                             ("tpf", 48, '1/2', 100_000), ("quad", 424, '1/3', 9_000),
                                              ("lat", 212, '1/3', 20_000), ("lat", 752, '1/2', 3_000),
                                              ("quad", 752, '1/2', 6_000), ("quad", 848, '1/3', 5_000)])
 def test_randomised_large_batch_vs_oracle(kernel, N, rate, B):

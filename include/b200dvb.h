@@ -223,6 +223,10 @@ int b200dvb_debug_tpf_cycles(double *out8_h, int reset);
  * out-phase windows in shared memory, out-phase windows in tensor memory, hard decision, warp total}. */
 int b200dvb_debug_nii_cycles(double *out8_h, int reset);
 
+/* Same for the low-latency kernel (cycles of thread 0 of each CTA): {tables + de-puncture, P0 record build, P1 the two
+ * recursions, P2 a-posteriori maxima + extrinsic, hard decision, CTA total, 0, 0}. */
+int b200dvb_debug_lat_cycles(double *out8_h, int reset);
+
 /* Process-wide development switches (never needed in production).
  *   B200DVB_DBG_MF_VARIANT  matched-filter kernel: 0 = default, 1 = double-buffered cp.async staging, 2 = round-1 kernel
  *   B200DVB_DBG_MAP_VARIANT complex64 mapper: 0 = per-order choice, 1 = one symbol per lane, 2 = four consecutive symbols per lane */

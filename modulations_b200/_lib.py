@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200dvb_debug_set_option": (_c_int, [_c_int, _c_int]),
     "b200dvb_debug_tpf_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_debug_nii_cycles": (_c_int, [_c_void_p, _c_int]),
+    "b200dvb_debug_lat_cycles": (_c_int, [_c_void_p, _c_int]),
     "b200dvb_tmem_selftest": (_c_int, [_c_void_p]),
     "b200dvb_microbench": (_c_int, [_c_void_p]),
     "b200dvb_microbench2": (_c_int, [_c_void_p]),

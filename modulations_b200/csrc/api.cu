@@ -455,6 +455,12 @@ int b200dvb_debug_nii_cycles(double *out8_h, int reset)
     return nii_read_phase_cycles(out8_h, reset);
 }
 
+int b200dvb_debug_lat_cycles(double *out8_h, int reset)
+{
+    if (!out8_h) return B200DVB_EINVAL;
+    return lat_read_phase_cycles(out8_h, reset);
+}
+
 int b200dvb_debug_set_option(int option, int value)
 {
     switch (option) {

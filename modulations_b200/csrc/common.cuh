@@ -125,6 +125,7 @@ int nii_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
                       void *ws, size_t ws_bytes, cudaStream_t s);
 size_t nii_workspace_bytes(const Codec &c, int B);
 int nii_read_phase_cycles(double *out_h, int reset);
+int lat_read_phase_cycles(double *out_h, int reset);
 int read_phase_cycles(double *out_h, int reset);
 
 int launch_encode(const Codec &c, int B, const uint8_t *info, uint8_t *coded, uint8_t *circ,

@@ -62,9 +62,15 @@ __device__ __forceinline__ void ld8(const float *p, float (&g)[8])
 }
 
 
+// phase timers (SM cycles of thread 0, summed over CTAs): 0 tables + de-puncture, 1 P0, 2 P1, 3 P2, 4 hard decision, 5 total
+__device__ unsigned long long g_lat_cycles[8];
+
+template <bool TIMED>
 __global__ void __launch_bounds__(kLatThreads)
 lat_kernel(const LatArgs A)
 {
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = TIMED ? clock64() : 0;
     extern __shared__ __align__(16) unsigned char sm[];
     const int N = A.N, tid = threadIdx.x;
     // shared-memory frame: [perm | inv] int16, then per couple: L1, L2 (float4), Le1, Le2, Y (double2), record (8 floats),
@@ -88,6 +94,7 @@ lat_kernel(const LatArgs A)
 
     for (int frame = blockIdx.x; frame < A.B; frame += gridDim.x) {
         __syncthreads();
+        long long tA = TIMED ? clock64() : 0;
         const float *row = A.llr + (size_t)frame * A.llr_stride;
         for (int i = tid; i < 2 * N; i += kLatThreads) perm[i] = A.tab[i];
         if (tid < 2) s_err[tid] = 0;
@@ -102,6 +109,7 @@ lat_kernel(const LatArgs A)
             L2[k] = make_float4(__ldg(row + op), __ldg(row + op + 1), o2 >= 0 ? __ldg(row + o2) : 0.f, o3 >= 0 ? __ldg(row + o3) : 0.f);
         }
         __syncthreads();
+        if (TIMED) { const long long t = clock64(); ph[0] += t - tA; tA = t; }
         for (int h = 0; h < 2 * A.iterations; ++h) {
             const bool second = (h & 1) != 0, first = h == 0;
             const double sf = (h >> 1) < A.iterations - 1 ? A.sf_inner : A.sf_last;
@@ -118,6 +126,7 @@ lat_kernel(const LatArgs A)
                 reinterpret_cast<float4 *>(rec + 8 * k)[1] = make_float4(g[4], g[5], g[6], g[7]);
             }
             __syncthreads();
+            if (TIMED) { const long long t = clock64(); ph[1] += t - tA; tA = t; }
             // ---- P1: the two recursions, twice around the circular trellis (:162-230) ----
             // One state per lane (16 lanes of a warp, the upper half-warp mirrors the lower): the new metric of a state
             // needs two old ones and the normaliser n[0] two more, so a step is 4 shuffles -> 2 x (add, add, max) ->
@@ -183,6 +192,7 @@ lat_kernel(const LatArgs A)
                 }
             }
             __syncthreads();
+            if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
             // ---- P2: a-posteriori maxima and the float64 extrinsic (:232-281) ----
             double2 *LeOut = second ? Le2 : Le1;
             for (int k = tid; k < N; k += kLatThreads) {
@@ -197,6 +207,7 @@ lat_kernel(const LatArgs A)
                 LeOut[k] = make_double2(ea, eb);
             }
             __syncthreads();
+            if (TIMED) { const long long t = clock64(); ph[3] += t - tA; tA = t; }
         }
         // ---- hard decision (:526-537) + optional error counting ----
         int my_err = 0;
@@ -225,10 +236,27 @@ lat_kernel(const LatArgs A)
             atomicAdd(A.counters + 2, 1ull);
             atomicAdd(A.counters + 3, 2ull * N);
         }
+        if (TIMED) { const long long t = clock64(); ph[4] += t - tA; tA = t; }
+    }
+    if (TIMED && tid == 0) {
+        ph[5] = clock64() - t_begin;
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_lat_cycles[i], (unsigned long long)ph[i]);
     }
 }
 
 }  // namespace
+
+int lat_read_phase_cycles(double *out_h, int reset)
+{
+    unsigned long long h[8];
+    B2_CUDA(cudaMemcpyFromSymbol(h, g_lat_cycles, sizeof h));
+    for (int i = 0; i < 8; ++i) out_h[i] = (double)h[i];
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        B2_CUDA(cudaMemcpyToSymbol(g_lat_cycles, z, sizeof z));
+    }
+    return B200DVB_OK;
+}
 
 size_t lat_smem_bytes(int N)
 {
@@ -245,12 +273,13 @@ int lat_configure(Codec &c)
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
     const size_t need = lat_smem_bytes(c.N);
     cudaFuncAttributes fa;
-    B2_CUDA(cudaFuncGetAttributes(&fa, lat_kernel));
+    B2_CUDA(cudaFuncGetAttributes(&fa, lat_kernel<false>));
     const size_t cap = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;   // the static words count against the limit
     if (need > cap) return B200DVB_OK;
-    B2_CUDA(cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     int occ = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel, kLatThreads, need));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel<false>, kLatThreads, need));
     if (occ < 1) return B200DVB_OK;
     c.lat_enabled = 1;
     c.lat_frames_per_wave = (occ < 2 ? occ : 2) * prop.multiProcessorCount;   // at most two CTAs per SM: one lone thread per scheduler
@@ -266,7 +295,8 @@ int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed; A.ref_bits = ref_bits; A.counters = counters;
     const int grid = B < c.lat_frames_per_wave ? B : c.lat_frames_per_wave;
-    lat_kernel<<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
+    if (c.opt_phase_timers) lat_kernel<true><<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
+    else                    lat_kernel<false><<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

@@ -70,6 +70,12 @@ if "latvar" in which:
             one = llr[:1].contiguous()
             best, med = timeit(lambda: c.decode_batch(one, out="packed"))
             print(f"N={N:4d} R={rate} variant {var}: {best*1e3:8.1f} us (median {med*1e3:8.1f})  bit-exact vs quad: {ok}")
+            c.handle.set_option(_lib.OPT_PHASE_TIMERS, 1)
+            ph = np.zeros(8); lib.b200dvb_debug_lat_cycles(_lib.host_ptr(ph), 1)
+            c.decode_batch(one, out="packed"); torch.cuda.synchronize()
+            lib.b200dvb_debug_lat_cycles(_lib.host_ptr(ph), 1)
+            c.handle.set_option(_lib.OPT_PHASE_TIMERS, 0)
+            print("        cycles: setup %d  P0 %d  P1 %d  P2 %d  hard %d  total %d  (per SISO: P0 %.0f P1 %.0f P2 %.0f)" % (*ph[:6], ph[1]/16, ph[2]/16, ph[3]/16))
 
 if "long" in which:
     print("# long frames (table N), 8 it, resident, B sized to ~4 waves; % of the 64 ACS/clk/SM roofline at 1965 MHz")

@@ -5,16 +5,12 @@
 // Why a third kernel.  A frame is 16 SISOs of strictly sequential recursions: the throughput kernels amortise that
 // over 64 frames per SM, and a batch of ONE frame then costs what a full wave costs (thread-per-frame kernel: 0.99 ms
 // at N=212; quad kernel: 0.65 ms; profiles/r02_measure_pack1.txt).  Here everything that is NOT sequential is spread
-// over the 256 threads of a CTA, and the two recursions run as two lone warps, one state metric per lane (4 shuffles +
-// 7 FP32 operations per step: 77 cycles, against 120 for one thread holding all 16 states, whose 63 operations are
-// issue-bound), and the second lap of a recursion stops as soon as it has provably re-joined the first:
+// over the 256 threads of a CTA, and the two recursions run on four warps with one state metric per lane (4 shuffles +
+// 7 FP32 operations per step: ~80 cycles, against 120 for one thread holding all 16 states, whose 63 operations are
+// issue-bound), their first lap cut into four speculative segments and the second lap ended where it has provably
+// re-joined the first:
 //   P0 (all threads, one trellis step each): a-priori gather, Y = Lc + La in float64, the merged branch-metric record;
-//   P1 (two warps): warp A runs alpha around the circular trellis, storing alpha[k]; the second lap (:182-183: it
-//       starts from the first lap's end state) overwrites them and STOPS where its 16 metrics equal, bit for bit,
-//       what the first lap stored at that position: from there on it would reproduce the first lap (deterministic
-//       recursion, same inputs), whose values are already in place.  Exact; on noisy N=212 codewords the laps
-//       re-join after 40 steps on average (p99: 108, measured with the oracle), so a SISO is ~N + 50 sequential
-//       steps instead of 2 N.  Warp B does the same for beta (natural state labels), concurrently;
+//   P1 (four warps): `segmented_recursion` below — exact, ~N/4 + 48 + 50 sequential steps per SISO instead of 2 N;
 //   P2 (all threads, one step each): the 64 a-posteriori sums of a step and the float64 extrinsic epilogue.
 // The whole frame lives in shared memory (240 bytes per couple: 51 KB at N=212, 204 KB at N=848), so the same kernel
 // serves every N of the reference's table.  It is a latency path, not a throughput path: api.cu dispatches batches
@@ -29,6 +25,8 @@ namespace {
 using namespace tpf;
 
 constexpr int kLatThreads = 256;
+constexpr int kSegs = 4;            // lap-1 segments per direction: two warps, two segments per warp (one per half-warp)
+constexpr int kWarm = 64;           // warm-up steps of a speculative segment
 
 struct LatArgs {
     int N, B, iterations, n_llr, num_sms;
@@ -62,11 +60,146 @@ __device__ __forceinline__ void ld8(const float *p, float (&g)[8])
 }
 
 
+// ---- P1: one recursion (alpha, or beta in natural labels), SEGMENTED, one state metric per lane -----------------------
+// The reference runs every recursion twice around the circular trellis: lap 1 from zeros, lap 2 from lap 1's end state
+// (:167-183, :203-217); what it keeps is lap 2.  Two observations make that short here, both EXACT:
+//  (1) the recursion is deterministic, so two runs over the same records that hold the same 16 metrics, bit for bit, at
+//      one position hold the same metrics at every later position;
+//  (2) runs started from different states re-join quickly (measured with the oracle: after 40 steps on average at N=212,
+//      p99 108) because max-log survivors merge and the per-step normalisation removes the common offset.
+// Phase A: kSegs runs of lap 1 proceed concurrently.  Segment 0 starts from zeros at position 0 — the reference's own
+// lap 1; segment j > 0 starts from zeros kWarm steps before its first position, a GUESS that has usually re-joined the
+// true lap 1 by the time the segment begins.  Each stores the metrics of its own positions and leaves its end state in
+// shared memory.  All runs are equally long (L = (N + 3 kWarm) / 4 steps); two of them share a warp (one per half-warp:
+// same direction, so both address streams advance by the same compile-time stride).
+// Phase B: ONE warp carries the true trajectory.  It holds the true state at the start of segment 1 (the end state of
+// segment 0); if that equals what segment 1 stored there, segment 1 and its end state are the true ones by (1) and the
+// carrier jumps to the next boundary; if not, it recomputes and overwrites until its state equals the stored one (or
+// the segment ends).  After the last segment it holds the true lap-1 end state and runs lap 2 from position 0 the same
+// way: it stops where it has re-joined lap 1.  Every jump is taken on verified bitwise equality, so the stored metrics
+// are exactly the reference's lap 2 whatever the guesses were; a frame whose runs never re-join costs two full laps.
+// Sequential steps per SISO at N=212: ~101 (phase A) + ~50 (lap 2) + a few boundary checks, against 2 N = 424.
+// Logical position i = 0 .. N-1 in recursion order: trellis step k = i (alpha) or N-1-i (beta).
+// Per step: 4 shuffles -> 2 x (add, add, max) -> subtract: 77 - 80 cycles, of which 59 are the bare dependent chain
+// (shuffle ~36 + add + max + subtract; timing-only builds), against ~120 issue cycles when one thread holds all 16
+// states.  Measured slower: exchanging the metrics through shared memory (+10 %), hand-ordered schedules (+3 .. +14 %),
+// alpha and beta of a segment on the two halves of one warp (per-lane stride: +45 % per step), eight warps in phase A
+// (the SM's shuffle + shared-memory issue rate binds: 122 cycles per step).
+template <bool BETA>
+struct LaneRec {
+    int N, la, lb, l0b, ps;
+    bool swp;
+    const float2 *rp, *r0;
+    float *cells;                                                    // alpha: Al, beta: Be + 16; cell of step k at 16 k
+    __device__ __forceinline__ void init(float *cells_, const float *rec, int N_, int tid)
+    {
+        const int s = tid & 15;
+        // alpha: state s = 2t + b is fed by v[t], v[8+t]; beta: state s = 8 hi + t by z[2t], z[2t+1] (tpf_core.cuh)
+        const int t = BETA ? (s & 7) : (s >> 1);
+        N = N_; cells = cells_; ps = s;
+        la = BETA ? 2 * t : t; lb = BETA ? 2 * t + 1 : 8 + t; l0b = BETA ? 1 : 8;
+        swp = (((t >> 2) ^ (BETA ? (s >> 3) : s)) & 1) != 0;         // the metric added to the first operand is the odd entry
+        rp = reinterpret_cast<const float2 *>(rec) + cls(t);
+        r0 = reinterpret_cast<const float2 *>(rec);
+    }
+    __device__ __forceinline__ int kk(int i) const { return BETA ? N - 1 - i : i; }
+    __device__ __forceinline__ float step(float v, float2 pc, float2 p0) const
+    {
+        const float a = __shfl_sync(0xffffffffu, v, la, 16), bq = __shfl_sync(0xffffffffu, v, lb, 16);
+        const float v0 = __shfl_sync(0xffffffffu, v, 0, 16), v8 = __shfl_sync(0xffffffffu, v, l0b, 16);
+        const float X = swp ? pc.y : pc.x, Yv = swp ? pc.x : pc.y;
+        return f_sub(f_max(f_add(a, X), f_add(bq, Yv)), f_max(f_add(v0, p0.x), f_add(v8, p0.y)));
+    }
+    // phase A, TWO segments per warp (lanes 0-15 one, lanes 16-31 the next): from zeros at this lane's i0, `trips`
+    // steps (warp-uniform), storing from step tstore on while i < i1.  Returns the state at i1.  (A short last segment
+    // keeps stepping past i1 on records it does not use: the record array is padded and everything stays inside this
+    // CTA's shared memory.)
+    __device__ __forceinline__ float run2(int i0, int tstore, int i1, int trips) const
+    {
+        float v = 0.f, vend = 0.f;
+        const float2 *q = rp + 4 * kk(i0), *q0 = r0 + 4 * kk(i0);
+        float *cell = cells + 16 * kk(i0) + ps;
+        constexpr int D = BETA ? -1 : 1;
+        float2 pc = q[0], p0 = q0[0];
+        for (int t = 0; t < trips; ++t) {
+            const float2 pn = q[4 * D * (t + 1)], p0n = q0[4 * D * (t + 1)];
+            if (t >= tstore && i0 + t < i1) cell[16 * D * t] = v;
+            v = step(v, pc, p0);
+            vend = (i0 + t + 1 == i1) ? v : vend;
+            pc = pn; p0 = p0n;
+        }
+        return vend;
+    }
+    // phase B: carry the true state v from position i0 towards i1, overwriting, until it equals the stored state.
+    // Returns true when it re-joined (then the stored metrics from there to the end of the run they belong to are the
+    // true ones); v is the true state at i1 otherwise.  (The upper half-warp mirrors the lower.)
+    __device__ __forceinline__ bool carry(float &v, int i0, int i1) const
+    {
+        if (i0 >= i1) return false;
+        float2 pc = rp[4 * kk(i0)], p0 = r0[4 * kk(i0)];
+        bool joined = false;
+        for (int i = i0; i < i1; ++i) {
+            if (joined) return true;                                 // (tested one step late: the vote stays off the chain)
+            const int kn = kk(i + 1 < i1 ? i + 1 : i);
+            const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
+            float *cell = cells + 16 * kk(i) + ps;
+            joined = __all_sync(0xffffffffu, __float_as_uint(*cell) == __float_as_uint(v));
+            *cell = v;
+            v = step(v, pc, p0);
+            pc = pn; p0 = p0n;
+        }
+        return joined;
+    }
+};
+
+// segment boundaries: segment 0 is L steps long, segment j > 0 L - kWarm after kWarm warm-up steps: all runs take L steps
+__device__ __forceinline__ int seg_len(int N) { return (N + (kSegs - 1) * kWarm + kSegs - 1) / kSegs; }
+__device__ __forceinline__ int seg_start(int j, int N)
+{
+    if (j <= 0) return 0;
+    if (j >= kSegs) return N;
+    const int L = seg_len(N);
+    if (L <= kWarm) return N;                                        // short frames: segment 0 is the whole lap
+    const int p = L + (j - 1) * (L - kWarm);
+    return p < N ? p : N;
+}
+
+// warps 2 d and 2 d + 1 of the CTA serve direction d (0 alpha, 1 beta); wd = 0 / 1 is the warp's index in the direction
+template <bool BETA>
+__device__ __forceinline__ void segmented_recursion(float *cells, const float *rec, int N, int wd, int tid, float *es /* [kSegs][16] */)
+{
+    LaneRec<BETA> R;
+    R.init(cells, rec, N, tid);
+    // ---- phase A: segments 2 wd (lanes 0-15) and 2 wd + 1 (lanes 16-31) ----
+    {
+        const int j = 2 * wd + ((tid >> 4) & 1);
+        const int p0 = seg_start(j, N), p1 = seg_start(j + 1, N);
+        const int i0 = j == 0 ? 0 : (p0 > kWarm ? p0 - kWarm : 0);
+        const int L = seg_len(N);
+        const int trips = L <= kWarm ? (wd == 0 ? N : 0) : L;       // (warp-uniform)
+        // ONE call for the whole warp (it shuffles): a half-warp without a segment walks along segment 0 and stores nothing
+        const bool has = p0 < p1;
+        const float v = R.run2(has ? i0 : 0, has ? p0 - i0 : (1 << 30), has ? p1 : 0, trips);
+        if (has) es[16 * j + R.ps] = v;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(BETA ? 2 : 1) : "memory");   // the two warps of this direction
+    if (wd != 0) return;
+    // ---- phase B (first warp of the direction) ----
+    float v = es[R.ps];                                              // true state at the end of segment 0
+    for (int seg = 1; seg < kSegs; ++seg) {
+        const int q0 = seg_start(seg, N), q1 = seg_start(seg + 1, N);
+        if (q0 >= q1) continue;
+        if (R.carry(v, q0, q1)) v = es[16 * seg + R.ps];             // re-joined: this segment's end state is the true one
+    }
+    R.carry(v, 0, N);                                                // lap 2 (:182-183 / :216-217)
+}
+
+
 // phase timers (SM cycles of thread 0, summed over CTAs): 0 tables + de-puncture, 1 P0, 2 P1, 3 P2, 4 hard decision, 5 total
 __device__ unsigned long long g_lat_cycles[8];
 
 template <bool TIMED>
-__global__ void __launch_bounds__(kLatThreads)
+__global__ void __launch_bounds__(kLatThreads, 2)
 lat_kernel(const LatArgs A)
 {
     long long ph[6] = {0, 0, 0, 0, 0, 0};
@@ -83,15 +216,12 @@ lat_kernel(const LatArgs A)
     double2 *Le1 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
     double2 *Le2 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
     double2 *Y = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
-    float *rec = reinterpret_cast<float *>(p); p += (size_t)N * 32;
+    float *rec = reinterpret_cast<float *>(p) + 8; p += (size_t)(N + 2) * 32;   // (one pad record on either side)
     float *Al = reinterpret_cast<float *>(p); p += (size_t)N * 64;
     float *Be = reinterpret_cast<float *>(p); p += (size_t)(N + 1) * 64;
     unsigned *words = reinterpret_cast<unsigned *>(p);              // packed hard decisions, ceil(2N/32) words
     __shared__ int s_err[2];
-    // the two lone recursion threads sit in different warps (= different schedulers); a second CTA on the same SM
-    // uses the other two schedulers
-    const int wa = ((blockIdx.x / A.num_sms) & 1) ? 64 : 0, wb = wa + 32;
-
+    __shared__ float s_es[2 * kSegs * 16];                          // end states of the lap-1 segments, per direction
     for (int frame = blockIdx.x; frame < A.B; frame += gridDim.x) {
         __syncthreads();
         long long tA = TIMED ? clock64() : 0;
@@ -127,70 +257,9 @@ lat_kernel(const LatArgs A)
             }
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[1] += t - tA; tA = t; }
-            // ---- P1: the two recursions, twice around the circular trellis (:162-230) ----
-            // One state per lane (16 lanes of a warp, the upper half-warp mirrors the lower): the new metric of a state
-            // needs two old ones and the normaliser n[0] two more, so a step is 4 shuffles -> 2 x (add, add, max) ->
-            // subtract: a chain of dependent latencies instead of the ~120 issue cycles one thread needs for all 16
-            // states.  Same operations on the same operands as tpf::pass_step / tpf::bwd_step, so the bits agree.
-            // The second lap stops where it has re-joined the first: the recursion is deterministic, so once the 16
-            // metrics of lap 2 equal, bit for bit, what lap 1 left at the same trellis position, every later position
-            // of lap 2 would reproduce lap 1's values, which are already in place.  Measured with the oracle on
-            // N=212 noisy codewords: re-joined after 40 steps on average (p99 108); a lap that never re-joins runs
-            // to the end as before.  Exact, not an approximation: the exit is taken on verified equality only.
-            // Measured (profiles/r02_latency.txt): 77 cycles per step, of which 59 are the bare dependent chain (shuffle
-            // ~36 + add + max + subtract; timing-only builds without the bookkeeping).  Exchanging the metrics through
-            // the shared-memory cell they are stored in anyway was 10 % slower than the shuffles, and hand-ordered
-            // schedules (shuffles first; bookkeeping in the shadow of the arithmetic; loads made dependent on an add)
-            // all lost 3-14 % to the compiler's: a load issued after the shuffles holds the adds back.
-            if ((tid >> 5) == (wa >> 5)) {
-                const int s = tid & 15, t = s >> 1, c2 = 2 * cls(t);
-                const bool swp = (((t >> 2) ^ s) & 1) != 0;         // X (for v[t]) is the odd entry of the class pair
-                const float2 *rp = reinterpret_cast<const float2 *>(rec) + (c2 >> 1);
-                const float2 *r0 = reinterpret_cast<const float2 *>(rec);
-                float v = 0.f;
-                float2 pc = rp[0], p0 = r0[0];
-                for (int lap = 0; lap < 2; ++lap) {
-                    bool joined = false;
-                    for (int k = 0; k < N; ++k) {
-                        if (joined) break;                          // (tested one step late: the vote stays off the chain)
-                        const int kn = k + 1 < N ? k + 1 : 0;
-                        const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
-                        if (lap) joined = __all_sync(0xffffffffu, __float_as_uint(Al[16 * k + s]) == __float_as_uint(v));
-                        if ((tid & 16) == 0) Al[16 * k + s] = v;
-                        const float a = __shfl_sync(0xffffffffu, v, t, 16), bq = __shfl_sync(0xffffffffu, v, 8 + t, 16);
-                        const float v0 = __shfl_sync(0xffffffffu, v, 0, 16), v8 = __shfl_sync(0xffffffffu, v, 8, 16);
-                        const float X = swp ? pc.y : pc.x, Yv = swp ? pc.x : pc.y;
-                        const float n = f_max(f_add(a, X), f_add(bq, Yv));
-                        const float n0 = f_max(f_add(v0, p0.x), f_add(v8, p0.y));
-                        v = f_sub(n, n0);
-                        pc = pn; p0 = p0n;
-                    }
-                }
-            } else if ((tid >> 5) == (wb >> 5)) {
-                const int s = tid & 15, t = s & 7, c2 = 2 * cls(t);
-                const bool swp = (((t >> 2) ^ (s >> 3)) & 1) != 0;
-                const float2 *rp = reinterpret_cast<const float2 *>(rec) + (c2 >> 1);
-                const float2 *r0 = reinterpret_cast<const float2 *>(rec);
-                float z = 0.f;
-                float2 pc = rp[4 * (N - 1)], p0 = r0[4 * (N - 1)];
-                for (int lap = 0; lap < 2; ++lap) {
-                    bool joined = false;
-                    for (int k = N - 1; k >= 0; --k) {
-                        if (joined) break;
-                        const int kn = k > 0 ? k - 1 : N - 1;
-                        const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
-                        if (lap) joined = __all_sync(0xffffffffu, __float_as_uint(Be[16 * (k + 1) + s]) == __float_as_uint(z));
-                        if ((tid & 16) == 0) Be[16 * (k + 1) + s] = z;
-                        const float a = __shfl_sync(0xffffffffu, z, 2 * t, 16), bq = __shfl_sync(0xffffffffu, z, 2 * t + 1, 16);
-                        const float z0 = __shfl_sync(0xffffffffu, z, 0, 16), z1 = __shfl_sync(0xffffffffu, z, 1, 16);
-                        const float X = swp ? pc.y : pc.x, Yv = swp ? pc.x : pc.y;
-                        const float n = f_max(f_add(a, X), f_add(bq, Yv));
-                        const float n0 = f_max(f_add(z0, p0.x), f_add(z1, p0.y));
-                        z = f_sub(n, n0);
-                        pc = pn; p0 = p0n;
-                    }
-                }
-            }
+            // ---- P1: the two recursions, twice around the circular trellis (:162-230): segmented_recursion above ----
+            if (tid < 64) segmented_recursion<false>(Al, rec, N, tid >> 5, tid, s_es);
+            else if (tid < 128) segmented_recursion<true>(Be + 16, rec, N, (tid >> 5) - 2, tid, s_es + kSegs * 16);
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
             // ---- P2: a-posteriori maxima and the float64 extrinsic (:232-281) ----
@@ -260,7 +329,7 @@ int lat_read_phase_cycles(double *out_h, int reset)
 
 size_t lat_smem_bytes(int N)
 {
-    return (((size_t)4 * N + 15) / 16) * 16 + (size_t)N * (16 + 16 + 16 + 16 + 16 + 32 + 64) + (size_t)(N + 1) * 64 +
+    return (((size_t)4 * N + 15) / 16) * 16 + (size_t)N * (16 + 16 + 16 + 16 + 16 + 32 + 64) + 64 + (size_t)(N + 1) * 64 +
            (size_t)((2 * N + 31) / 32) * 4 + 64;
 }
 

@@ -77,6 +77,7 @@ struct Codec {
     int opt_kernel = 0;           // 0: automatic choice per batch, 1: quad kernel, 2: thread-per-frame kernel, 3: low-latency kernel
     int opt_no_row_staging = 0;   // 1: thread-per-frame transposition without the cp.async row staging
     int opt_phase_timers = 0;     // 1: run the kernel instances that keep per-phase cycle counters
+    int lat_pad = 0;              // low-latency kernel: conflict-free (padded) shared-memory strides fit for this N
     int lat_enabled = 0, lat_frames_per_wave = 0;   // low-latency kernel (decode_lat.cu): usable for this N; frames it takes at once
     int opt_mode = 0;             // decoder arithmetic: 0 = parity (the reference's), 1 = non-parity "nii" (B200DVB_MODE_NII)
     // device tables

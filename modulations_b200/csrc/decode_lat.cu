@@ -85,7 +85,7 @@ __device__ __forceinline__ void ld8(const float *p, float (&g)[8])
 // states.  Measured slower: exchanging the metrics through shared memory (+10 %), hand-ordered schedules (+3 .. +14 %),
 // alpha and beta of a segment on the two halves of one warp (per-lane stride: +45 % per step), eight warps in phase A
 // (the SM's shuffle + shared-memory issue rate binds: 122 cycles per step).
-template <bool BETA>
+template <bool BETA, int CS, int RS>   // CS / RS: floats between the metric cells / the records of consecutive steps
 struct LaneRec {
     int N, la, lb, l0b, ps;
     bool swp;
@@ -117,13 +117,13 @@ struct LaneRec {
     __device__ __forceinline__ float run2(int i0, int tstore, int i1, int trips) const
     {
         float v = 0.f, vend = 0.f;
-        const float2 *q = rp + 4 * kk(i0), *q0 = r0 + 4 * kk(i0);
-        float *cell = cells + 16 * kk(i0) + ps;
+        const float2 *q = rp + (RS / 2) * kk(i0), *q0 = r0 + (RS / 2) * kk(i0);
+        float *cell = cells + CS * kk(i0) + ps;
         constexpr int D = BETA ? -1 : 1;
         float2 pc = q[0], p0 = q0[0];
         for (int t = 0; t < trips; ++t) {
-            const float2 pn = q[4 * D * (t + 1)], p0n = q0[4 * D * (t + 1)];
-            if (t >= tstore && i0 + t < i1) cell[16 * D * t] = v;
+            const float2 pn = q[(RS / 2) * D * (t + 1)], p0n = q0[(RS / 2) * D * (t + 1)];
+            if (t >= tstore && i0 + t < i1) cell[CS * D * t] = v;
             v = step(v, pc, p0);
             vend = (i0 + t + 1 == i1) ? v : vend;
             pc = pn; p0 = p0n;
@@ -136,13 +136,13 @@ struct LaneRec {
     __device__ __forceinline__ bool carry(float &v, int i0, int i1) const
     {
         if (i0 >= i1) return false;
-        float2 pc = rp[4 * kk(i0)], p0 = r0[4 * kk(i0)];
+        float2 pc = rp[(RS / 2) * kk(i0)], p0 = r0[(RS / 2) * kk(i0)];
         bool joined = false;
         for (int i = i0; i < i1; ++i) {
             if (joined) return true;                                 // (tested one step late: the vote stays off the chain)
             const int kn = kk(i + 1 < i1 ? i + 1 : i);
-            const float2 pn = rp[4 * kn], p0n = r0[4 * kn];
-            float *cell = cells + 16 * kk(i) + ps;
+            const float2 pn = rp[(RS / 2) * kn], p0n = r0[(RS / 2) * kn];
+            float *cell = cells + CS * kk(i) + ps;
             joined = __all_sync(0xffffffffu, __float_as_uint(*cell) == __float_as_uint(v));
             *cell = v;
             v = step(v, pc, p0);
@@ -165,10 +165,10 @@ __device__ __forceinline__ int seg_start(int j, int N)
 }
 
 // warps 2 d and 2 d + 1 of the CTA serve direction d (0 alpha, 1 beta); wd = 0 / 1 is the warp's index in the direction
-template <bool BETA>
+template <bool BETA, int CS, int RS>
 __device__ __forceinline__ void segmented_recursion(float *cells, const float *rec, int N, int wd, int tid, float *es /* [kSegs][16] */)
 {
-    LaneRec<BETA> R;
+    LaneRec<BETA, CS, RS> R;
     R.init(cells, rec, N, tid);
     // ---- phase A: segments 2 wd (lanes 0-15) and 2 wd + 1 (lanes 16-31) ----
     {
@@ -198,10 +198,15 @@ __device__ __forceinline__ void segmented_recursion(float *cells, const float *r
 // phase timers (SM cycles of thread 0, summed over CTAs): 0 tables + de-puncture, 1 P0, 2 P1, 3 P2, 4 hard decision, 5 total
 __device__ unsigned long long g_lat_cycles[8];
 
-template <bool TIMED>
+// PAD: metric cells 20 instead of 16 floats apart and records 12 instead of 8, so that the position-parallel phases
+// (thread k reads the 64-byte cell and the 32-byte record of step k with LDS.128) are free of bank conflicts: with
+// strides of 16 / 8 words eight lanes hit two / four bank groups and P2 ran at 3 700 cycles per SISO instead of 1 500
+// (ncu: its samples sit on the adds behind those loads).  Costs 48 bytes per couple: frames beyond N ~ 780 use PAD = false.
+template <bool TIMED, bool PAD>
 __global__ void __launch_bounds__(kLatThreads, 2)
 lat_kernel(const LatArgs A)
 {
+    constexpr int CS = PAD ? 20 : 16, RS = PAD ? 12 : 8;
     long long ph[6] = {0, 0, 0, 0, 0, 0};
     const long long t_begin = TIMED ? clock64() : 0;
     extern __shared__ __align__(16) unsigned char sm[];
@@ -216,9 +221,9 @@ lat_kernel(const LatArgs A)
     double2 *Le1 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
     double2 *Le2 = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
     double2 *Y = reinterpret_cast<double2 *>(p); p += (size_t)N * 16;
-    float *rec = reinterpret_cast<float *>(p) + 8; p += (size_t)(N + 2) * 32;   // (one pad record on either side)
-    float *Al = reinterpret_cast<float *>(p); p += (size_t)N * 64;
-    float *Be = reinterpret_cast<float *>(p); p += (size_t)(N + 1) * 64;
+    float *rec = reinterpret_cast<float *>(p) + RS; p += (size_t)(N + 2) * RS * 4;   // (one pad record on either side)
+    float *Al = reinterpret_cast<float *>(p); p += (size_t)N * CS * 4;
+    float *Be = reinterpret_cast<float *>(p); p += (size_t)(N + 1) * CS * 4;
     unsigned *words = reinterpret_cast<unsigned *>(p);              // packed hard decisions, ceil(2N/32) words
     __shared__ int s_err[2];
     __shared__ float s_es[2 * kSegs * 16];                          // end states of the lap-1 segments, per direction
@@ -252,23 +257,23 @@ lat_kernel(const LatArgs A)
                 float g[8];
                 make_record(YA, YB, x.z, x.w, g);
                 Y[k] = make_double2(YA, YB);
-                reinterpret_cast<float4 *>(rec + 8 * k)[0] = make_float4(g[0], g[1], g[2], g[3]);
-                reinterpret_cast<float4 *>(rec + 8 * k)[1] = make_float4(g[4], g[5], g[6], g[7]);
+                reinterpret_cast<float4 *>(rec + RS * k)[0] = make_float4(g[0], g[1], g[2], g[3]);
+                reinterpret_cast<float4 *>(rec + RS * k)[1] = make_float4(g[4], g[5], g[6], g[7]);
             }
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[1] += t - tA; tA = t; }
             // ---- P1: the two recursions, twice around the circular trellis (:162-230): segmented_recursion above ----
-            if (tid < 64) segmented_recursion<false>(Al, rec, N, tid >> 5, tid, s_es);
-            else if (tid < 128) segmented_recursion<true>(Be + 16, rec, N, (tid >> 5) - 2, tid, s_es + kSegs * 16);
+            if (tid < 64) segmented_recursion<false, CS, RS>(Al, rec, N, tid >> 5, tid, s_es);
+            else if (tid < 128) segmented_recursion<true, CS, RS>(Be + CS, rec, N, (tid >> 5) - 2, tid, s_es + kSegs * 16);
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
             // ---- P2: a-posteriori maxima and the float64 extrinsic (:232-281) ----
             double2 *LeOut = second ? Le2 : Le1;
             for (int k = tid; k < N; k += kLatThreads) {
                 float x[16], zs[16], g[8], uv[4];
-                ld16(Al + 16 * k, x);
-                ld16(Be + 16 * (k + 1), zs);
-                ld8(rec + 8 * k, g);
+                ld16(Al + CS * k, x);
+                ld16(Be + CS * (k + 1), zs);
+                ld8(rec + RS * k, g);
                 ext_step(x, zs, g, uv);
                 const double2 y = Y[k];
                 double ea, eb;
@@ -327,10 +332,22 @@ int lat_read_phase_cycles(double *out_h, int reset)
     return B200DVB_OK;
 }
 
-size_t lat_smem_bytes(int N)
+static size_t lat_smem(int N, bool pad)
 {
-    return (((size_t)4 * N + 15) / 16) * 16 + (size_t)N * (16 + 16 + 16 + 16 + 16 + 32 + 64) + 64 + (size_t)(N + 1) * 64 +
-           (size_t)((2 * N + 31) / 32) * 4 + 64;
+    const size_t cs = pad ? 20 : 16, rs = pad ? 12 : 8;
+    return (((size_t)4 * N + 15) / 16) * 16 + (size_t)N * (16 + 16 + 16 + 16 + 16) + (size_t)(N + 2) * rs * 4 +
+           (size_t)N * cs * 4 + (size_t)(N + 1) * cs * 4 + (size_t)((2 * N + 31) / 32) * 4 + 64;
+}
+size_t lat_smem_bytes(int N) { return lat_smem(N, false); }
+
+static size_t lat_cap()
+{
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, lat_kernel<false, false>) != cudaSuccess) return 0;
+    return (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;   // the static words count against the limit
 }
 
 int lat_configure(Codec &c)
@@ -340,18 +357,20 @@ int lat_configure(Codec &c)
     cudaDeviceProp prop;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaGetDeviceProperties(&prop, dev));
-    const size_t need = lat_smem_bytes(c.N);
-    cudaFuncAttributes fa;
-    B2_CUDA(cudaFuncGetAttributes(&fa, lat_kernel<false>));
-    const size_t cap = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;   // the static words count against the limit
-    if (need > cap) return B200DVB_OK;
-    B2_CUDA(cudaFuncSetAttribute(lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-    B2_CUDA(cudaFuncSetAttribute(lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    const size_t cap = lat_cap();
+    if (lat_smem(c.N, false) > cap) return B200DVB_OK;
+    c.lat_pad = lat_smem(c.N, true) <= cap;
+    const size_t need = lat_smem(c.N, c.lat_pad != 0);
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    B2_CUDA(cudaFuncSetAttribute(lat_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     int occ = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel<false>, kLatThreads, need));
+    if (c.lat_pad) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel<false, true>, kLatThreads, need));
+    else           B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lat_kernel<false, false>, kLatThreads, need));
     if (occ < 1) return B200DVB_OK;
     c.lat_enabled = 1;
-    c.lat_frames_per_wave = (occ < 2 ? occ : 2) * prop.multiProcessorCount;   // at most two CTAs per SM: one lone thread per scheduler
+    c.lat_frames_per_wave = (occ < 2 ? occ : 2) * prop.multiProcessorCount;   // at most two CTAs per SM
     return B200DVB_OK;
 }
 
@@ -364,8 +383,14 @@ int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed; A.ref_bits = ref_bits; A.counters = counters;
     const int grid = B < c.lat_frames_per_wave ? B : c.lat_frames_per_wave;
-    if (c.opt_phase_timers) lat_kernel<true><<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
-    else                    lat_kernel<false><<<grid, kLatThreads, lat_smem_bytes(c.N), s>>>(A);
+    const size_t smem = lat_smem(c.N, c.lat_pad != 0);
+    if (c.lat_pad) {
+        if (c.opt_phase_timers) lat_kernel<true, true><<<grid, kLatThreads, smem, s>>>(A);
+        else                    lat_kernel<false, true><<<grid, kLatThreads, smem, s>>>(A);
+    } else {
+        if (c.opt_phase_timers) lat_kernel<true, false><<<grid, kLatThreads, smem, s>>>(A);
+        else                    lat_kernel<false, false><<<grid, kLatThreads, smem, s>>>(A);
+    }
     B2_CUDA(cudaGetLastError());
     return B200DVB_OK;
 }

@@ -151,6 +151,7 @@ int launch_matched_filter(size_t n, const void *x, const double *taps_h, int nta
                           size_t n_out, void *out, cudaStream_t s);
 
 void set_mf_variant(int v);
+void set_lat_warm(int v);
 void set_map_variant(int v);
 int modem_build_pwl(Modem &m);
 int run_microbench(double *results_h);

@@ -26,10 +26,10 @@ using namespace tpf;
 
 constexpr int kLatThreads = 256;
 constexpr int kSegs = 4;            // lap-1 segments per direction: two warps, two segments per warp (one per half-warp)
-constexpr int kWarm = 64;           // warm-up steps of a speculative segment
+constexpr int kWarmDefault = 64;    // warm-up steps of a speculative segment (LatArgs.warm; development: B200DVB_DBG_LAT_WARM)
 
 struct LatArgs {
-    int N, B, iterations, n_llr, num_sms;
+    int N, B, iterations, n_llr, num_sms, warm;
     double sf_inner, sf_last;
     const int16_t *tab;             // [7][N]: perm, inv_perm, offA, offW1, offY1, offW2, offY2
     const float *llr;
@@ -153,12 +153,12 @@ struct LaneRec {
 };
 
 // segment boundaries: segment 0 is L steps long, segment j > 0 L - kWarm after kWarm warm-up steps: all runs take L steps
-__device__ __forceinline__ int seg_len(int N) { return (N + (kSegs - 1) * kWarm + kSegs - 1) / kSegs; }
-__device__ __forceinline__ int seg_start(int j, int N)
+__device__ __forceinline__ int seg_len(int N, int kWarm) { return (N + (kSegs - 1) * kWarm + kSegs - 1) / kSegs; }
+__device__ __forceinline__ int seg_start(int j, int N, int kWarm)
 {
     if (j <= 0) return 0;
     if (j >= kSegs) return N;
-    const int L = seg_len(N);
+    const int L = seg_len(N, kWarm);
     if (L <= kWarm) return N;                                        // short frames: segment 0 is the whole lap
     const int p = L + (j - 1) * (L - kWarm);
     return p < N ? p : N;
@@ -166,16 +166,16 @@ __device__ __forceinline__ int seg_start(int j, int N)
 
 // warps 2 d and 2 d + 1 of the CTA serve direction d (0 alpha, 1 beta); wd = 0 / 1 is the warp's index in the direction
 template <bool BETA, int CS, int RS>
-__device__ __forceinline__ void segmented_recursion(float *cells, const float *rec, int N, int wd, int tid, float *es /* [kSegs][16] */)
+__device__ __forceinline__ void segmented_recursion(float *cells, const float *rec, int N, int kWarm, int wd, int tid, float *es /* [kSegs][16] */)
 {
     LaneRec<BETA, CS, RS> R;
     R.init(cells, rec, N, tid);
     // ---- phase A: segments 2 wd (lanes 0-15) and 2 wd + 1 (lanes 16-31) ----
     {
         const int j = 2 * wd + ((tid >> 4) & 1);
-        const int p0 = seg_start(j, N), p1 = seg_start(j + 1, N);
+        const int p0 = seg_start(j, N, kWarm), p1 = seg_start(j + 1, N, kWarm);
         const int i0 = j == 0 ? 0 : (p0 > kWarm ? p0 - kWarm : 0);
-        const int L = seg_len(N);
+        const int L = seg_len(N, kWarm);
         const int trips = L <= kWarm ? (wd == 0 ? N : 0) : L;       // (warp-uniform)
         // ONE call for the whole warp (it shuffles): a half-warp without a segment walks along segment 0 and stores nothing
         const bool has = p0 < p1;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void segmented_recursion(float *cells, const float *r
     // ---- phase B (first warp of the direction) ----
     float v = es[R.ps];                                              // true state at the end of segment 0
     for (int seg = 1; seg < kSegs; ++seg) {
-        const int q0 = seg_start(seg, N), q1 = seg_start(seg + 1, N);
+        const int q0 = seg_start(seg, N, kWarm), q1 = seg_start(seg + 1, N, kWarm);
         if (q0 >= q1) continue;
         if (R.carry(v, q0, q1)) v = es[16 * seg + R.ps];             // re-joined: this segment's end state is the true one
     }
@@ -263,8 +263,8 @@ lat_kernel(const LatArgs A)
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[1] += t - tA; tA = t; }
             // ---- P1: the two recursions, twice around the circular trellis (:162-230): segmented_recursion above ----
-            if (tid < 64) segmented_recursion<false, CS, RS>(Al, rec, N, tid >> 5, tid, s_es);
-            else if (tid < 128) segmented_recursion<true, CS, RS>(Be + CS, rec, N, (tid >> 5) - 2, tid, s_es + kSegs * 16);
+            if (tid < 64) segmented_recursion<false, CS, RS>(Al, rec, N, A.warm, tid >> 5, tid, s_es);
+            else if (tid < 128) segmented_recursion<true, CS, RS>(Be + CS, rec, N, A.warm, (tid >> 5) - 2, tid, s_es + kSegs * 16);
             __syncthreads();
             if (TIMED) { const long long t = clock64(); ph[2] += t - tA; tA = t; }
             // ---- P2: a-posteriori maxima and the float64 extrinsic (:232-281) ----
@@ -332,6 +332,9 @@ int lat_read_phase_cycles(double *out_h, int reset)
     return B200DVB_OK;
 }
 
+static int g_lat_warm = kWarmDefault;
+void set_lat_warm(int v) { g_lat_warm = v; }
+
 static size_t lat_smem(int N, bool pad)
 {
     const size_t cs = pad ? 20 : 16, rs = pad ? 12 : 8;
@@ -379,7 +382,7 @@ int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
 {
     if (B == 0) return B200DVB_OK;
     LatArgs A{};
-    A.N = c.N; A.B = B; A.iterations = c.iterations; A.n_llr = c.n_llr; A.num_sms = c.num_sms;
+    A.N = c.N; A.B = B; A.iterations = c.iterations; A.n_llr = c.n_llr; A.num_sms = c.num_sms; A.warm = g_lat_warm;
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed; A.ref_bits = ref_bits; A.counters = counters;
     const int grid = B < c.lat_frames_per_wave ? B : c.lat_frames_per_wave;

@@ -65,11 +65,12 @@ if "latvar" in which:
         c = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="lat")
         info, llr = gen(c, 16)
         want = ref.decode_batch(llr)
-        for var in (0,):
+        for var in (32, 48, 64, 80, 96, 128):
+            _lib.check(lib.b200dvb_debug_set_option(3, var), "dbg")
             ok = bool(torch.equal(c.decode_batch(llr), want))
             one = llr[:1].contiguous()
             best, med = timeit(lambda: c.decode_batch(one, out="packed"))
-            print(f"N={N:4d} R={rate} variant {var}: {best*1e3:8.1f} us (median {med*1e3:8.1f})  bit-exact vs quad: {ok}")
+            print(f"N={N:4d} R={rate} warm-up {var:3d}: {best*1e3:8.1f} us (median {med*1e3:8.1f})  bit-exact vs quad: {ok}")
             c.handle.set_option(_lib.OPT_PHASE_TIMERS, 1)
             ph = np.zeros(8); lib.b200dvb_debug_lat_cycles(_lib.host_ptr(ph), 1)
             c.decode_batch(one, out="packed"); torch.cuda.synchronize()

@@ -232,7 +232,7 @@ int b200dvb_debug_lat_cycles(double *out8_h, int reset);
  *   B200DVB_DBG_MAP_VARIANT complex64 mapper: 0 = per-order choice, 1 = one symbol per lane, 2 = four consecutive symbols per lane */
 #define B200DVB_DBG_MF_VARIANT 1
 #define B200DVB_DBG_MAP_VARIANT 2
-#define B200DVB_DBG_LAT_WARM 3     /* low-latency kernel: warm-up steps of a speculative lap-1 segment (default 64); any value is exact */
+#define B200DVB_DBG_LAT_WARM 3     /* low-latency kernel: warm-up steps of a speculative lap-1 segment (0 = default, 40 + N/16 within [48, 96]); any value is exact */
 int b200dvb_debug_set_option(int option, int value);
 
 /* Diagnostics: round trip through tensor memory (tcgen05.alloc/st/ld/dealloc) between the

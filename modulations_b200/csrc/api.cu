@@ -469,7 +469,7 @@ int b200dvb_debug_set_option(int option, int value)
         set_mf_variant(value);
         return B200DVB_OK;
     case B200DVB_DBG_LAT_WARM:
-        if (value < 1 || value > 1024) return B200DVB_EINVAL;
+        if (value < 0 || value > 1024) return B200DVB_EINVAL;
         set_lat_warm(value);
         return B200DVB_OK;
     case B200DVB_DBG_MAP_VARIANT:

@@ -26,7 +26,9 @@ using namespace tpf;
 
 constexpr int kLatThreads = 256;
 constexpr int kSegs = 4;            // lap-1 segments per direction: two warps, two segments per warp (one per half-warp)
-constexpr int kWarmDefault = 64;    // warm-up steps of a speculative segment (LatArgs.warm; development: B200DVB_DBG_LAT_WARM)
+// warm-up steps of a speculative segment (LatArgs.warm): 40 + N/16 within [48, 96] — measured optimum 48 at N=212, 80 - 96
+// at N=752 (profiles/r02_lat_warmup.txt; every value gives the same bits); development override: B200DVB_DBG_LAT_WARM
+static int lat_warm_for(int N) { const int w = 40 + N / 16; return w < 48 ? 48 : (w > 96 ? 96 : w); }
 
 struct LatArgs {
     int N, B, iterations, n_llr, num_sms, warm;
@@ -332,7 +334,7 @@ int lat_read_phase_cycles(double *out_h, int reset)
     return B200DVB_OK;
 }
 
-static int g_lat_warm = kWarmDefault;
+static int g_lat_warm = 0;         // 0: lat_warm_for(N)
 void set_lat_warm(int v) { g_lat_warm = v; }
 
 static size_t lat_smem(int N, bool pad)
@@ -382,7 +384,7 @@ int lat_launch_decode(const Codec &c, int B, const float *llr, long long llr_str
 {
     if (B == 0) return B200DVB_OK;
     LatArgs A{};
-    A.N = c.N; A.B = B; A.iterations = c.iterations; A.n_llr = c.n_llr; A.num_sms = c.num_sms; A.warm = g_lat_warm;
+    A.N = c.N; A.B = B; A.iterations = c.iterations; A.n_llr = c.n_llr; A.num_sms = c.num_sms; A.warm = g_lat_warm > 0 ? g_lat_warm : lat_warm_for(c.N);
     A.sf_inner = c.sf_inner; A.sf_last = c.sf_last; A.tab = c.d_tab;
     A.llr = llr; A.llr_stride = llr_stride; A.bits = bits; A.packed = packed; A.ref_bits = ref_bits; A.counters = counters;
     const int grid = B < c.lat_frames_per_wave ? B : c.lat_frames_per_wave;

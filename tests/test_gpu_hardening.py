@@ -203,3 +203,27 @@ def test_low_latency_kernel_lap_rejoin_edge_cases(N, rate):
     x[20:24] = np.clip(rng.randn(4, n) * 40.0, -50, 50)
     ref = o.decode_batch(x, threads=os.cpu_count() or 1)
     assert np.array_equal(g.decode_batch(x), ref)
+
+
+@pytest.mark.parametrize("N,rate", [(64, '1/3'), (212, '1/3'), (424, '1/2')])
+def test_low_latency_kernel_is_exact_for_any_warmup(N, rate):
+    """The low-latency kernel runs lap 1 of a recursion in four segments; three of them start from a GUESS (zeros W steps
+    before the segment) that one carrier warp then verifies against the true trajectory, bit for bit, recomputing
+    wherever the guess had not re-joined it (decode_lat.cu).  The result must therefore not depend on W: W = 1 (nearly
+    every guess wrong: the carrier recomputes almost the whole lap), odd values, W > N (a single segment) — all equal
+    to the oracle."""
+    from modulations_b200 import _lib
+    from modulations_b200 import dvb_rcs2_turbo as turbo
+    lib = _lib.load()
+    g = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="lat")
+    o = oracle.OracleTurbo(N, rate, 8, perm=g.perm, inv_perm=g.inv_perm)
+    info, llr = _mc(g, 48, 2.0, 77 + N)
+    x = llr.cpu().numpy()
+    x[40:] = np.random.RandomState(N).randn(8, x.shape[1]).astype(np.float32) * 3.0      # pure noise: slow re-joins
+    ref = o.decode_batch(x, threads=os.cpu_count() or 1)
+    try:
+        for W in (1, 2, 7, 33, 64, 200, 1024):
+            _lib.check(lib.b200dvb_debug_set_option(3, W), "debug_set_option")
+            assert np.array_equal(g.decode_batch(x), ref), f"warm-up {W}"
+    finally:
+        _lib.check(lib.b200dvb_debug_set_option(3, 0), "debug_set_option")

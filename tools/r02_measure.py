@@ -65,7 +65,7 @@ if "latvar" in which:
         c = turbo.DVBRCS2_Turbo(N, rate, 8, kernel="lat")
         info, llr = gen(c, 16)
         want = ref.decode_batch(llr)
-        for var in (32, 48, 64, 80, 96, 128):
+        for var in (32, 48, 64, 80, 96, 128, 0):
             _lib.check(lib.b200dvb_debug_set_option(3, var), "dbg")
             ok = bool(torch.equal(c.decode_batch(llr), want))
             one = llr[:1].contiguous()

@@ -533,8 +533,8 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(30):
             t0 = time.perf_counter(); codec.decode(x1); ts.append(time.perf_counter() - t0)
         lat = {"decode_single_frame_us": float(np.median(ts) * 1e6), "what": "DVBRCS2_Turbo.decode(numpy llr) wall clock, "
-               "median of 30 (H2D + one launch + D2H); batches of up to two CTAs per SM run on the one-CTA-per-frame kernel "
-               "(decode_lat.cu), batches up to one quad-kernel wave on the quad kernel, larger ones thread-per-frame"}
+               "median of 30 (H2D + one launch + D2H); small batches (up to min(6, N/50) passes of two CTAs per SM) run on the one-CTA-per-frame "
+               "kernel (decode_lat.cu), batches up to one quad-kernel wave on the quad kernel, larger ones thread-per-frame"}
         for Bq in (1, 148, 256, 4096, 65536):
             xq = llr[:Bq]
             lat[f"resident_B{Bq}_us"] = time_kernel(lambda: codec.decode_batch(xq, out="packed"), reps=5, warm=2) * 1e3

@@ -242,13 +242,15 @@ int b200dvb_siso(b200dvb_codec_t codec, int B, const float *Lc_A, const float *L
 // 16-frame tile takes as long as a full wave (64 frames per SM); the quad kernel finishes a wave of 32 frames per
 // SM in 0.72x that time (profiles/r02_measure_pack1.txt: 0.75 ms against 1.05 ms at N=212), so batches that fit one
 // quad wave go there.  A pure function of (codec, B): the workspace query and the launch agree.
-// Batches of up to two frames per SM take the low-latency kernel (one CTA per frame: 0.26 ms per frame at N=212 against
-// 0.65 ms for a quad wave), whatever N.
+// Small batches take the low-latency kernel (one CTA per frame, two CTAs per SM while the frame fits twice): a pass
+// over up to lat_frames_per_wave frames takes 0.11 / 0.155 / 0.29 ms at N = 48 / 212 / 752, a quad-kernel wave 0.15 /
+// 0.65 - 0.76 / 1.84 ms, so up to min(6, N / 50) passes of it beat one quad wave (profiles/r02_latency.txt).
+static int lat_passes(const Codec &c) { const int p = c.N / 50; return p < 1 ? 1 : (p > 6 ? 6 : p); }
 static bool use_lat(const Codec &c, int B)
 {
     if (!c.lat_enabled) return false;
     if (c.opt_kernel == 3) return true;
-    return c.opt_kernel == 0 && B <= c.lat_frames_per_wave;
+    return c.opt_kernel == 0 && (long long)B <= (long long)lat_passes(c) * c.lat_frames_per_wave;
 }
 
 static bool use_tpf(const Codec &c, int B)

@@ -72,3 +72,24 @@ def test_nii16_emulator_matches_its_model(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-2000:]
     assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 20
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"),
+                    reason="needs nvcc to compile the host side of tpf_core.cuh")
+def test_lat_emulator_matches_oracle(tmp_path):
+    """The low-latency kernel (decode_lat.cu): one state metric per lane (per-lane operand / record selection), lap 1
+    of each recursion in four speculative segments verified by a carrier, lap 2 ended where it re-joins lap 1 —
+    replayed on the CPU with the kernel's arithmetic core for warm-up lengths from 1 (nearly every guess wrong) to
+    beyond N (one segment), against oracle/turbo_oracle.c bit for bit."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    orc = tmp_path / "orc.o"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-c", os.path.join(ROOT, "oracle", "turbo_oracle.c"), "-o", str(orc)],
+                   check=True)
+    emu_o = tmp_path / "lat_emu.o"
+    subprocess.run([nvcc, "-O1", "--fmad=false", "-Xcompiler", "-ffp-contract=off", "-c",
+                    os.path.join(ROOT, "tools", "lat_emulator.cu"), "-o", str(emu_o)], check=True, capture_output=True)
+    exe = tmp_path / "lat_emu"
+    subprocess.run([nvcc, "-o", str(exe), str(emu_o), str(orc)], check=True, capture_output=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "FAIL" not in res.stdout and res.stdout.count(" ok ") >= 100

@@ -12,9 +12,10 @@
 //   P0 (all threads, one trellis step each): a-priori gather, Y = Lc + La in float64, the merged branch-metric record;
 //   P1 (four warps): `segmented_recursion` below — exact, ~N/4 + 48 + 50 sequential steps per SISO instead of 2 N;
 //   P2 (all threads, one step each): the 64 a-posteriori sums of a step and the float64 extrinsic epilogue.
-// The whole frame lives in shared memory (240 bytes per couple: 51 KB at N=212, 204 KB at N=848), so the same kernel
-// serves every N of the reference's table.  It is a latency path, not a throughput path: api.cu dispatches batches
-// of up to a few hundred frames here, larger ones to the wave kernels.
+// The whole frame lives in shared memory (288 bytes per couple with conflict-free strides: 61 KB at N=212, 217 KB at
+// N=752; 240 bytes per couple beyond N ~ 780: 204 KB at N=848), so the same kernel serves every N of the reference's
+// table.  It is a latency path, not a throughput path: api.cu dispatches batches of up to min(6, N/50) passes of two
+// CTAs per SM here (1 184 frames at N=212), larger ones to the wave kernels.
 #include "common.cuh"
 #include "tpf_core.cuh"
 

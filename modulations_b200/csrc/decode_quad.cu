@@ -408,6 +408,17 @@ struct Feed {
     }
 };
 
+// does every lane of the warp hold, bit for bit, what checkpoint idx holds?
+template <class CK>
+__device__ __forceinline__ bool rejoined(const CK &ck, int idx, const float (&r)[4])
+{
+    float o[4];
+    ck.load(idx, o);
+    const bool eq = __float_as_uint(o[0]) == __float_as_uint(r[0]) && __float_as_uint(o[1]) == __float_as_uint(r[1]) &&
+                    __float_as_uint(o[2]) == __float_as_uint(r[2]) && __float_as_uint(o[3]) == __float_as_uint(r[3]);
+    return __all_sync(0xffffffffu, eq);
+}
+
 template <bool PF, class CK>
 __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const CK &ck, float *xch, float *rings,
                                           int warp, int xslot, const Lane &L, long long &t_mid)
@@ -433,17 +444,29 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (warp == 0) {
         // pass 1 (convergence, :167-179) from zeros, then alpha[0] <- alpha[N] (:182-183)
+        // GREC (long frames): pass 1 leaves its own checkpoints over [0, M) and keeps alpha[M]; pass 2 then stops at the
+        // first checkpoint where the 8 frames of the warp hold, bit for bit, what pass 1 held there — from that point
+        // on it would only reproduce pass 1 (same records, deterministic recursion), whose checkpoints are in place.
+        // Exact (a warp that never re-joins runs all of pass 2); the second laps re-join after ~50 steps on average
+        // (decode_lat.cu), pass 2 is N/2 steps.
+        float rM[4] = {0.f, 0.f, 0.f, 0.f};
         G2 cur = pair_at(0);
 #pragma unroll 2
         for (int k = 0; k < N; k += 2) {
             const G2 nxt = pair_at(k + 2 < N ? k + 2 : 0);
+            if (PF) {
+                if ((k & (kWin - 1)) == 0 && k < M) ck.store(k / kWin, r);
+                if (k == M) { rM[0] = r[0]; rM[1] = r[1]; rM[2] = r[2]; rM[3] = r[3]; }
+            }
             stepg(r, cur.a0, cur.b0);
             stepg(r, cur.a1, cur.b1);
             transpose_fwd(r, x.next(), L);
             cur = nxt;
         }
+        if (PF) ck.publish();                               // (the stores above are complete before pass 2 reads them back)
         // pass 2 up to the crossing point M (a multiple of kWin), checkpoint every kWin steps
         for (int k = 0; k < M; k += kWin) {
+            if (PF && rejoined(ck, k / kWin, r)) { r[0] = rM[0]; r[1] = rM[1]; r[2] = rM[2]; r[3] = rM[3]; break; }
             ck.store(k / kWin, r);
 #pragma unroll
             for (int j = 0; j < kWin; j += 2) {
@@ -456,29 +479,41 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
         }
     } else {
         // beta pass 1 (:203-213): j = N..2, then beta[N] <- beta[0] (:216-217)
+        float rM[4] = {0.f, 0.f, 0.f, 0.f};
+        const int ragged = (N - M) & (kWin - 1);           // 0 or 4
         G2 cur = pair_at(N - 2);
 #pragma unroll 2
         for (int j = N; j > 0; j -= 2) {
             const G2 nxt = pair_at(j >= 4 ? j - 4 : N - 2);
+            if (PF) {                                       // (GREC: checkpoints of pass 1 over (M, N], see the alpha warp)
+                if (j > M && ((j - M) & (kWin - 1)) == 0) ck.store(g.nckA + (j - M) / kWin - 1, r);
+                if (ragged && j == N) ck.store(g.nckA + g.nckB - 1, r);
+                if (j == M) { rM[0] = r[0]; rM[1] = r[1]; rM[2] = r[2]; rM[3] = r[3]; }
+            }
             stepg(r, cur.a1, cur.b1);      // gamma[j-1] (odd)
             stepg(r, cur.a0, cur.b0);      // gamma[j-2] (even)
             transpose_bwd(r, x.next(), L);
             cur = nxt;
         }
+        if (PF) ck.publish();
         // pass 2 down to M: a checkpoint at the end of every alpha-warp window
         int j = N;
-        const int ragged = (N - M) & (kWin - 1);           // 0 or 4
+        bool done = false;
         if (ragged) {
-            ck.store(g.nckA + g.nckB - 1, r);
-            for (int t = 0; t < ragged; t += 2, j -= 2) {
-                const G2 nxt = pair_at(j - 4);
-                stepg(r, cur.a1, cur.b1);
-                stepg(r, cur.a0, cur.b0);
-                transpose_bwd(r, x.next(), L);
-                cur = nxt;
+            if (PF && rejoined(ck, g.nckA + g.nckB - 1, r)) done = true;
+            else {
+                ck.store(g.nckA + g.nckB - 1, r);
+                for (int t = 0; t < ragged; t += 2, j -= 2) {
+                    const G2 nxt = pair_at(j - 4);
+                    stepg(r, cur.a1, cur.b1);
+                    stepg(r, cur.a0, cur.b0);
+                    transpose_bwd(r, x.next(), L);
+                    cur = nxt;
+                }
             }
         }
-        for (; j > M; j -= kWin) {
+        for (; !done && j > M; j -= kWin) {
+            if (PF && rejoined(ck, g.nckA + (j - M) / kWin - 1, r)) { done = true; break; }
             ck.store(g.nckA + (j - M) / kWin - 1, r);
 #pragma unroll
             for (int t = 0; t < kWin; t += 2) {
@@ -489,6 +524,7 @@ __device__ __forceinline__ void siso_core(const QuadGeom &g, float *gam, const C
                 cur = nxt;
             }
         }
+        if (done) { r[0] = rM[0]; r[1] = rM[1]; r[2] = rM[2]; r[3] = rM[3]; }
     }
     if (PF) { q_cpa_wait<0>(); __syncwarp(); }
     ck.publish();

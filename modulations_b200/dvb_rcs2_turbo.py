@@ -395,6 +395,7 @@ class DVBRCS2_Turbo:
         self._punct_u8 = np.array([self.punct[k] for k in ('W1', 'Y1', 'W2', 'Y2')], np.uint8)
         self._handles = {}
         self._e2e = None
+        self._one = {}             # decode(): pinned staging + device buffers per (handle, stream)
 
     @property
     def iterations(self):
@@ -570,9 +571,34 @@ class DVBRCS2_Turbo:
         return out_host
 
     def decode(self, llr):
-        """Decode one frame of LLRs (positive = bit 0) into 2N info bits, int32 (:464-537)."""
+        """Decode one frame of LLRs (positive = bit 0) into 2N info bits, int32 (:464-537).
+
+        The reference's call shape (turbo_test_suite.py:138-164): one frame per call, so the host side counts.  Pinned
+        staging buffers and the device tensors are kept per (handle, stream); a call is one copy into pinned memory,
+        an asynchronous host-to-device copy, the kernel, an asynchronous copy back and one stream synchronisation.
+        Not re-entrant per object and stream (neither is the reference's numba decoder)."""
         llr = np.array(llr, dtype=np.float32)
-        return self.decode_batch(llr[None, :])[0]
+        torch = _lib.require_cuda()
+        h = self.handle
+        if llr.ndim != 1 or llr.shape[0] < h.n_llr or getattr(h.device, "type", "cuda") != "cuda":
+            return self.decode_batch(llr[None, :] if llr.ndim == 1 else llr)[0]      # (short input: raises like the batch path)
+        with torch.cuda.device(h.device):
+            st = torch.cuda.current_stream(h.device)
+            key = (h, st.cuda_stream)
+            one = self._one.get(key)
+            if one is None:
+                hin = torch.empty((1, h.n_llr), dtype=torch.float32, pin_memory=True)
+                hout = torch.empty((1, self.k_info), dtype=torch.int32, pin_memory=True)
+                one = (hin, hin.numpy(), torch.empty((1, h.n_llr), dtype=torch.float32, device=h.device),
+                       torch.empty((1, self.k_info), dtype=torch.int32, device=h.device), hout, hout.numpy())
+                self._one[key] = one
+            hin, hin_np, din, dbits, hout, hout_np = one
+            np.copyto(hin_np[0], llr[:h.n_llr])
+            din.copy_(hin, non_blocking=True)
+            h.decode(din, bits=dbits, stream=st)
+            hout.copy_(dbits, non_blocking=True)
+            st.synchronize()
+        return hout_np[0].copy()
 
 
 def _unpack_bits_device(packed, out_u8, k_info):
